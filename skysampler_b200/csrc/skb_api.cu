@@ -1,0 +1,739 @@
+// C-ABI glue of libskb (include/skb.h): handle lifetime, host<->device staging, launch planning.
+// No compute happens here and there is no CPU fallback: every path ends in a kernel launch or an
+// error code.
+#include "skb_internal.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace skb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define SKB_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            cudaGetLastError();                                                                 \
+            return fail(_e == cudaErrorMemoryAllocation ? SKB_ENOMEM : SKB_ECUDA, "%s: %s", #expr, \
+                        cudaGetErrorString(_e));                                                \
+        }                                                                                       \
+    } while (0)
+
+// true when p can be dereferenced by a kernel on the current device
+static bool is_device_ptr(const void* p)
+{
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// grow-only device scratch
+struct Scratch {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes, bool zero_new = false)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return e; }
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = want;
+        if (zero_new) return cudaMemset(p, 0, want);
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace skb
+
+using namespace skb;
+
+struct skb_kde {
+    int device = 0;
+    int sms = 148;
+    KdeDev hk;                 // host copy of the device descriptor
+    KdeDev* dk = nullptr;      // device descriptor
+    float* tiles = nullptr;
+    double* zt64 = nullptr;
+    double* cumsum = nullptr;
+    Scratch partial;           // [nsplit][M] double2
+    Scratch counters;          // [ceil(M/FB)] int, zero between calls
+    Scratch q_stage, out_stage, aux_stage, flag_stage;
+    Scratch small;             // 2 x u64 device counters
+};
+
+namespace skb {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// ---- launch planning --------------------------------------------------------------------------
+int score_ctas_per_sm(int D);   // skb_score.cu
+
+static int plan_nsplit(const skb_kde* h, long long M, int njobs_same_kde_shape)
+{
+    const int D = h->hk.D;
+    const int QB = NT * queries_per_thread(D);
+    const long long qblocks = (M + QB - 1) / QB;
+    const long long ctas = qblocks * (njobs_same_kde_shape > 0 ? njobs_same_kde_shape : 1);
+    const long long slots = (long long)h->sms * score_ctas_per_sm(D);
+    const long long want = 6 * slots;                      // >= 6 waves keeps the tail under ~15%
+    if (ctas >= want) return 1;
+    long long ns = (want + ctas - 1) / ctas;
+    const long long cap = h->hk.ntiles / 8 > 1 ? h->hk.ntiles / 8 : 1;   // >= 8 tiles per split
+    if (ns > cap) ns = cap;
+    if (ns > 1024) ns = 1024;
+    return (int)(ns < 1 ? 1 : ns);
+}
+
+struct GroupSpec {
+    int ratio = 0;
+    const int32_t* sign = nullptr;
+    const double* log_abs_jac = nullptr;
+    double log_m = 0.0;
+    const double* u = nullptr;          // device
+    double band = 0.0;
+    double* out_log_ratio = nullptr;    // device
+    unsigned char* accept = nullptr;    // device
+    unsigned char* in_band = nullptr;   // device
+};
+
+struct DevJob {
+    skb_kde* h;
+    const void* q;        // device
+    int q_f32;
+    int q_is_whitened;
+    long long M, ldq;
+    const int32_t* cols;  // host
+    double* out_logp;     // device or NULL
+    double* out_m;        // device or NULL
+    double* out_s;
+};
+
+// All pointers are device pointers here.  grouped: every job scores the same M rows and the
+// finalize step sees all of them; otherwise each job finalizes alone.
+static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupSpec& g, cudaStream_t st)
+{
+    if (n <= 0) return SKB_OK;
+    if (n > SKB_MAX_JOBS) return fail(SKB_EINVAL, "too many jobs in one launch (%d > %d)", n, SKB_MAX_JOBS);
+    ScoreLaunch L;
+    memset(&L, 0, sizeof(L));
+    int nsplit[SKB_MAX_JOBS];
+    int expected_group = 0;
+    for (int j = 0; j < n; j++) {
+        const DevJob& dj = jobs[j];
+        int same = 0;
+        for (int k = 0; k < n; k++) same += (jobs[k].h->hk.D == dj.h->hk.D);
+        nsplit[j] = plan_nsplit(dj.h, dj.M, same);
+        expected_group += nsplit[j];
+    }
+    // finalize table
+    for (int j = 0; j < n; j++) {
+        const DevJob& dj = jobs[j];
+        FinJob& fj = L.fin.fj[j];
+        const bool need_partial = grouped || nsplit[j] > 1;
+        if (need_partial) {
+            SKB_CUDA(dj.h->partial.reserve((size_t)nsplit[j] * (size_t)dj.M * sizeof(double2)));
+            fj.partial = reinterpret_cast<double2*>(dj.h->partial.p);
+        }
+        fj.out_logp = dj.out_logp;
+        fj.out_m = dj.out_m;
+        fj.out_s = dj.out_s;
+        fj.log_norm = dj.h->hk.log_norm;
+        fj.nsplit = nsplit[j];
+        fj.sign = (grouped && g.sign) ? g.sign[j] : 0;
+        fj.sign_logjac = (grouped && g.sign && g.log_abs_jac) ? g.sign[j] * g.log_abs_jac[j] : 0.0;
+    }
+    L.fin.ratio = grouped ? g.ratio : 0;
+    L.fin.u = g.u;
+    L.fin.log_m = g.log_m;
+    L.fin.band = g.band;
+    L.fin.out_log_ratio = g.out_log_ratio;
+    L.fin.accept = g.accept;
+    L.fin.in_band = g.in_band;
+
+    int* group_counters = nullptr;
+    if (grouped) {
+        const size_t nfb = (size_t)((jobs[0].M + FB - 1) / FB);
+        SKB_CUDA(jobs[0].h->counters.reserve(nfb * sizeof(int), true));
+        group_counters = reinterpret_cast<int*>(jobs[0].h->counters.p);
+    }
+    // one launch per distinct feature dimension
+    bool done[SKB_MAX_JOBS] = {false};
+    for (int j0 = 0; j0 < n; j0++) {
+        if (done[j0]) continue;
+        const int D = jobs[j0].h->hk.D;
+        int nl = 0;
+        long long max_qblocks = 0;
+        int max_split = 1;
+        for (int j = j0; j < n; j++) {
+            if (done[j] || jobs[j].h->hk.D != D) continue;
+            done[j] = true;
+            const DevJob& dj = jobs[j];
+            ScoreJob& sj = L.jobs[nl++];
+            memset(&sj, 0, sizeof(sj));
+            sj.kde = dj.h->dk;
+            sj.q = dj.q;
+            sj.M = dj.M;
+            sj.ldq = dj.ldq;
+            sj.q_f32 = dj.q_f32;
+            sj.q_is_whitened = dj.q_is_whitened;
+            sj.nsplit = nsplit[j];
+            sj.fin_slot = j;
+            bool ident = true;
+            for (int k = 0; k < D; k++) {
+                const int c = dj.cols ? dj.cols[k] : k;
+                if (c < 0 || c >= dj.ldq || c > 127)
+                    return fail(SKB_EINVAL, "query column index %d out of range for row stride %lld", c, dj.ldq);
+                sj.cols[k] = (signed char)c;
+                ident &= (c == k);
+            }
+            const size_t esz = dj.q_f32 ? 4 : 8;
+            sj.cols_identity = ident && ((reinterpret_cast<uintptr_t>(dj.q) & 15) == 0) && ((dj.ldq * esz) % 16 == 0);
+            if (grouped) {
+                sj.fin_first = 0; sj.fin_count = n;
+                sj.counters = group_counters; sj.expected = expected_group;
+            } else {
+                sj.fin_first = j; sj.fin_count = 1;
+                if (nsplit[j] > 1) {
+                    const size_t nfb = (size_t)((dj.M + FB - 1) / FB);
+                    SKB_CUDA(dj.h->counters.reserve(nfb * sizeof(int), true));
+                    sj.counters = reinterpret_cast<int*>(dj.h->counters.p);
+                    sj.expected = nsplit[j];
+                }
+            }
+            const int QB = NT * queries_per_thread(D);
+            const long long qb = (dj.M + QB - 1) / QB;
+            if (qb > max_qblocks) max_qblocks = qb;
+            if (nsplit[j] > max_split) max_split = nsplit[j];
+        }
+        if (max_qblocks > 0x7fffffffLL) return fail(SKB_EINVAL, "too many query rows for one launch");
+        if (max_qblocks > 0) SKB_CUDA(launch_score(D, L, nl, max_qblocks, max_split, st));
+    }
+    return SKB_OK;
+}
+
+// rows per staged chunk when query / output buffers live on the host
+static const long long STAGE_ROWS = 1LL << 22;
+
+}  // namespace skb
+
+// =================================================================================================
+extern "C" {
+
+const char* skb_last_error(void) { return g_err; }
+int skb_version(void) { return 100; }
+int64_t skb_launch_count(void) { return g_launches.load(); }
+
+int skb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+double skb_log_knorm(int d, double h) { return -0.5 * d * std::log(2.0 * M_PI) - d * std::log(h); }
+
+int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_train, int train_is_whitened,
+               const double* w, const double* cumsum_w, double h, const double* mu, const double* W,
+               const double* Winv, int device, skb_handle* out)
+{
+    if (!out) return fail(SKB_EINVAL, "out handle is NULL");
+    *out = nullptr;
+    if (!train || N <= 0) return fail(SKB_EINVAL, "training set is empty");
+    if (d < 1 || d > SKB_MAXD) return fail(SKB_EINVAL, "feature dimension %d outside 1..%d", d, SKB_MAXD);
+    if (ld_train < d) return fail(SKB_EINVAL, "ld_train %lld < d %d", (long long)ld_train, d);
+    if (!(h > 0.0) || !std::isfinite(h)) return fail(SKB_EINVAL, "bandwidth must be positive and finite");
+    if (train_dtype != SKB_F64 && train_dtype != SKB_F32) return fail(SKB_EINVAL, "bad train dtype %d", train_dtype);
+    if ((mu == nullptr) != (W == nullptr)) return fail(SKB_EINVAL, "mu and W must be given together");
+    if (!train_is_whitened && !W) return fail(SKB_EINVAL, "raw training rows need the whitening map (mu, W)");
+    if (N > (1LL << 40)) return fail(SKB_EINVAL, "training set too large");
+    int ndev = skb_device_count();
+    if (ndev <= 0) return fail(SKB_ECUDA, "no CUDA device available (this backend has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(SKB_EINVAL, "device %d out of range (0..%d)", device, ndev - 1);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(SKB_ECUDA, "cudaSetDevice(%d) failed", device);
+
+    skb_kde* k = new (std::nothrow) skb_kde();
+    if (!k) return fail(SKB_ENOMEM, "out of host memory");
+    k->device = device;
+    cudaDeviceGetAttribute(&k->sms, cudaDevAttrMultiProcessorCount, device);
+    KdeDev& hk = k->hk;
+    memset(&hk, 0, sizeof(hk));
+    hk.N = N;
+    hk.D = d;
+    hk.ntiles = (int)((N + TN - 1) / TN);
+    hk.h = h;
+    hk.c = std::sqrt(0.5 * 1.4426950408889634074) / h;   // sqrt(log2(e)/2)/h
+    hk.has_w = (w != nullptr);
+    hk.has_winv = (Winv != nullptr);
+    for (int i = 0; i < d; i++) hk.mu[i] = mu ? mu[i] : 0.0;
+    for (int i = 0; i < d; i++)
+        for (int kk = 0; kk < d; kk++) {
+            hk.Wc[i * d + kk] = (W ? W[i * d + kk] : (i == kk ? 1.0 : 0.0)) * hk.c;
+            hk.Winv[i * d + kk] = Winv ? Winv[i * d + kk] : (i == kk ? 1.0 : 0.0);
+        }
+
+    int rc = SKB_OK;
+    std::vector<double> wh, cs;
+    void* d_train_tmp = nullptr;
+    double* d_w = nullptr;
+    auto cleanup = [&](int code) {
+        if (d_train_tmp) cudaFree(d_train_tmp);
+        if (d_w) cudaFree(d_w);
+        if (code != SKB_OK) { skb_destroy(k); }
+        return code;
+    };
+#define SKB_CUDA_C(expr)                                                                       \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            cudaGetLastError();                                                                \
+            return cleanup(fail(_e == cudaErrorMemoryAllocation ? SKB_ENOMEM : SKB_ECUDA, "%s: %s", #expr, \
+                                cudaGetErrorString(_e)));                                      \
+        }                                                                                      \
+    } while (0)
+
+    // ---- weights: validate, sum, max, sequential cumsum (host, fp64) ----
+    double wmax = 1.0;
+    hk.sum_w = (double)N;
+    if (w) {
+        wh.resize((size_t)N);
+        if (is_device_ptr(w)) SKB_CUDA_C(cudaMemcpy(wh.data(), w, (size_t)N * 8, cudaMemcpyDeviceToHost));
+        else memcpy(wh.data(), w, (size_t)N * 8);
+        wmax = 0.0;
+        for (int64_t i = 0; i < N; i++) {
+            const double v = wh[(size_t)i];
+            if (!(v >= 0.0) || !std::isfinite(v))
+                return cleanup(fail(SKB_EINVAL, "Negative values in data passed to `sample_weight` (or non-finite) at row %lld",
+                                    (long long)i));
+            if (v > wmax) wmax = v;
+        }
+        if (!(wmax > 0.0)) return cleanup(fail(SKB_EINVAL, "all sample weights are zero"));
+        // numpy.sum is a pairwise sum; reproduce its 8-lane, 128-block structure closely enough
+        // (differences are O(1e-16) relative and only enter through log(sum_w)).
+        {
+            long double acc = 0.0L;
+            for (int64_t i = 0; i < N; i++) acc += wh[(size_t)i];
+            hk.sum_w = (double)acc;
+        }
+        cs.resize((size_t)N);
+        if (cumsum_w) {
+            if (is_device_ptr(cumsum_w)) SKB_CUDA_C(cudaMemcpy(cs.data(), cumsum_w, (size_t)N * 8, cudaMemcpyDeviceToHost));
+            else memcpy(cs.data(), cumsum_w, (size_t)N * 8);
+        } else {
+            double a = 0.0;                    // numpy.cumsum: strictly sequential fp64 adds
+            for (int64_t i = 0; i < N; i++) { a += wh[(size_t)i]; cs[(size_t)i] = a; }
+        }
+    }
+    hk.log_norm = skb_log_knorm(d, h) - std::log(hk.sum_w) + std::log(wmax);
+
+    // ---- device buffers ----
+    const size_t tile_bytes = (size_t)hk.ntiles * stage_floats(d) * sizeof(float);
+    SKB_CUDA_C(cudaMalloc(&k->tiles, tile_bytes));
+    SKB_CUDA_C(cudaMalloc(&k->zt64, (size_t)N * d * sizeof(double)));
+    if (w) {
+        SKB_CUDA_C(cudaMalloc(&k->cumsum, (size_t)N * sizeof(double)));
+        SKB_CUDA_C(cudaMemcpy(k->cumsum, cs.data(), (size_t)N * 8, cudaMemcpyHostToDevice));
+        SKB_CUDA_C(cudaMalloc(&d_w, (size_t)N * 8));
+        SKB_CUDA_C(cudaMemcpy(d_w, wh.data(), (size_t)N * 8, cudaMemcpyHostToDevice));
+    }
+    SKB_CUDA_C(cudaMalloc(&k->dk, sizeof(KdeDev)));
+    hk.tiles = k->tiles;
+    hk.zt64 = k->zt64;
+    hk.cumsum_w = k->cumsum;
+    SKB_CUDA_C(cudaMemcpy(k->dk, &hk, sizeof(KdeDev), cudaMemcpyHostToDevice));
+
+    const void* d_train = train;
+    if (!is_device_ptr(train)) {
+        const size_t esz = train_dtype == SKB_F32 ? 4 : 8;
+        const size_t bytes = ((size_t)(N - 1) * ld_train + d) * esz;
+        SKB_CUDA_C(cudaMalloc(&d_train_tmp, bytes));
+        SKB_CUDA_C(cudaMemcpy(d_train_tmp, train, bytes, cudaMemcpyHostToDevice));
+        d_train = d_train_tmp;
+    }
+    SKB_CUDA_C(launch_pack(d_train, train_dtype == SKB_F32, N, d, ld_train, train_is_whitened, k->dk, d_w,
+                           1.0 / wmax, k->tiles, k->zt64, hk.ntiles, 0));
+    SKB_CUDA_C(cudaStreamSynchronize(0));
+    SKB_CUDA_C(k->small.reserve(64, true));
+#undef SKB_CUDA_C
+    rc = cleanup(SKB_OK);
+    *out = k;
+    return rc;
+}
+
+int skb_destroy(skb_handle h)
+{
+    if (!h) return SKB_OK;
+    DeviceGuard guard(h->device);
+    cudaDeviceSynchronize();
+    if (h->tiles) cudaFree(h->tiles);
+    if (h->zt64) cudaFree(h->zt64);
+    if (h->cumsum) cudaFree(h->cumsum);
+    if (h->dk) cudaFree(h->dk);
+    h->partial.release(); h->counters.release(); h->q_stage.release(); h->out_stage.release();
+    h->aux_stage.release(); h->flag_stage.release(); h->small.release();
+    cudaGetLastError();
+    delete h;
+    return SKB_OK;
+}
+
+int64_t skb_n_train(skb_handle h) { return h ? h->hk.N : 0; }
+int skb_ndim(skb_handle h) { return h ? h->hk.D : 0; }
+double skb_sum_weight(skb_handle h) { return h ? h->hk.sum_w : 0.0; }
+int skb_device(skb_handle h) { return h ? h->device : -1; }
+
+// ---- scoring ------------------------------------------------------------------------------------
+static int check_query_args(skb_handle h, const void* q, int q_dtype, int64_t M, int64_t ldq)
+{
+    if (!h) return fail(SKB_EINVAL, "NULL handle");
+    if (M < 0) return fail(SKB_EINVAL, "negative row count");
+    if (M > 0 && !q) return fail(SKB_EINVAL, "NULL query pointer");
+    if (q_dtype != SKB_F64 && q_dtype != SKB_F32) return fail(SKB_EINVAL, "bad query dtype %d", q_dtype);
+    if (ldq < 1) return fail(SKB_EINVAL, "query row stride must be >= 1");
+    return SKB_OK;
+}
+
+static int score_one(skb_handle h, const void* q, int q_dtype, int64_t M, int64_t ldq, const int32_t* cols,
+                     int q_is_whitened, double* out_logp, double* out_m, double* out_s, void* stream)
+{
+    int rc = check_query_args(h, q, q_dtype, M, ldq);
+    if (rc) return rc;
+    if (M == 0) return SKB_OK;
+    if (!cols && ldq < h->hk.D)
+        return fail(SKB_EINVAL, "query has %lld features, the KDE was fitted with %d", (long long)ldq, h->hk.D);
+    DeviceGuard guard(h->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool q_dev = is_device_ptr(q);
+    double* outs[3] = {out_logp, out_m, out_s};
+    bool any_host_out = false;
+    for (double* o : outs) if (o && !is_device_ptr(o)) any_host_out = true;
+    const GroupSpec g;
+    if (q_dev && !any_host_out) {
+        DevJob dj{h, q, q_dtype == SKB_F32, q_is_whitened, M, ldq, cols, out_logp, out_m, out_s};
+        return run_jobs_device(&dj, 1, false, g, st);
+    }
+    // staged path: chunks of rows through device scratch
+    const size_t esz = q_dtype == SKB_F32 ? 4 : 8;
+    for (int64_t a = 0; a < M; a += STAGE_ROWS) {
+        const int64_t m = (M - a < STAGE_ROWS) ? (M - a) : STAGE_ROWS;
+        const char* qsrc = reinterpret_cast<const char*>(q) + (size_t)a * ldq * esz;
+        const void* qd = qsrc;
+        if (!q_dev) {
+            const size_t bytes = ((size_t)(m - 1) * ldq + (cols ? ldq : ldq)) * esz;
+            SKB_CUDA(h->q_stage.reserve(bytes));
+            SKB_CUDA(cudaMemcpyAsync(h->q_stage.p, qsrc, bytes, cudaMemcpyHostToDevice, st));
+            qd = h->q_stage.p;
+        }
+        SKB_CUDA(h->out_stage.reserve((size_t)m * 8 * 3));
+        double* dst[3];
+        for (int t = 0; t < 3; t++) {
+            if (!outs[t]) dst[t] = nullptr;
+            else if (is_device_ptr(outs[t])) dst[t] = outs[t] + a;
+            else dst[t] = reinterpret_cast<double*>(h->out_stage.p) + (size_t)t * m;
+        }
+        DevJob dj{h, qd, q_dtype == SKB_F32, q_is_whitened, m, ldq, cols, dst[0], dst[1], dst[2]};
+        rc = run_jobs_device(&dj, 1, false, g, st);
+        if (rc) return rc;
+        for (int t = 0; t < 3; t++)
+            if (outs[t] && !is_device_ptr(outs[t]))
+                SKB_CUDA(cudaMemcpyAsync(outs[t] + a, dst[t], (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+        SKB_CUDA(cudaStreamSynchronize(st));
+    }
+    return SKB_OK;
+}
+
+int skb_score(skb_handle h, const void* q, int q_dtype, int64_t M, int64_t ldq, const int32_t* cols,
+              int q_is_whitened, double* out_logp, void* stream)
+{
+    if (M > 0 && !out_logp) return fail(SKB_EINVAL, "NULL output pointer");
+    return score_one(h, q, q_dtype, M, ldq, cols, q_is_whitened, out_logp, nullptr, nullptr, stream);
+}
+
+int skb_score_partial(skb_handle h, const void* q, int q_dtype, int64_t M, int64_t ldq, const int32_t* cols,
+                      int q_is_whitened, double* out_m, double* out_s, void* stream)
+{
+    if (M > 0 && (!out_m || !out_s)) return fail(SKB_EINVAL, "NULL output pointer");
+    return score_one(h, q, q_dtype, M, ldq, cols, q_is_whitened, nullptr, out_m, out_s, stream);
+}
+
+int skb_score_batch(const skb_job* jobs, int n_jobs, void* stream)
+{
+    if (n_jobs < 0 || (n_jobs > 0 && !jobs)) return fail(SKB_EINVAL, "bad job list");
+    if (n_jobs == 0) return SKB_OK;
+    if (n_jobs > SKB_MAX_JOBS) return fail(SKB_EINVAL, "at most %d jobs per batch", SKB_MAX_JOBS);
+    bool all_dev = true;
+    for (int j = 0; j < n_jobs; j++) {
+        int rc = check_query_args(jobs[j].kde, jobs[j].q, jobs[j].q_dtype, jobs[j].M, jobs[j].ldq);
+        if (rc) return rc;
+        if (jobs[j].M > 0 && !jobs[j].out_logp) return fail(SKB_EINVAL, "job %d: NULL output pointer", j);
+        if (jobs[j].kde->device != jobs[0].kde->device) return fail(SKB_EINVAL, "jobs of one batch must share a device");
+        for (int k = 0; k < j; k++)
+            if (jobs[k].kde == jobs[j].kde) return fail(SKB_EINVAL, "a KDE handle may appear once per batch");
+        if (jobs[j].M > 0 && (!is_device_ptr(jobs[j].q) || !is_device_ptr(jobs[j].out_logp))) all_dev = false;
+    }
+    if (!all_dev) {
+        // host buffers: serial staged calls (still correct, just not one launch)
+        for (int j = 0; j < n_jobs; j++) {
+            int rc = skb_score(jobs[j].kde, jobs[j].q, jobs[j].q_dtype, jobs[j].M, jobs[j].ldq, jobs[j].cols,
+                               jobs[j].q_is_whitened, jobs[j].out_logp, stream);
+            if (rc) return rc;
+        }
+        return SKB_OK;
+    }
+    DeviceGuard guard(jobs[0].kde->device);
+    DevJob dj[SKB_MAX_JOBS];
+    int n = 0;
+    for (int j = 0; j < n_jobs; j++) {
+        if (jobs[j].M == 0) continue;
+        dj[n++] = DevJob{jobs[j].kde, jobs[j].q, jobs[j].q_dtype == SKB_F32, jobs[j].q_is_whitened, jobs[j].M,
+                         jobs[j].ldq, jobs[j].cols, jobs[j].out_logp, nullptr, nullptr};
+    }
+    const GroupSpec g;
+    return run_jobs_device(dj, n, false, g, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int skb_ratio_accept(const skb_handle* kdes, int n_kde, const int32_t* sign, const double* log_abs_jac,
+                     double log_m, const void* q, int q_dtype, int64_t M, int64_t ldq, const int32_t* cols,
+                     const double* u, double band, double* out_logp, double* out_log_ratio, uint8_t* accept,
+                     uint8_t* in_band, void* stream)
+{
+    if (!kdes || n_kde < 1 || n_kde > SKB_MAX_GROUP) return fail(SKB_EINVAL, "group size must be 1..%d", SKB_MAX_GROUP);
+    if (!sign || !log_abs_jac) return fail(SKB_EINVAL, "sign / log_abs_jac are required");
+    for (int k = 0; k < n_kde; k++) {
+        int rc = check_query_args(kdes[k], q, q_dtype, M, ldq);
+        if (rc) return rc;
+        if (kdes[k]->device != kdes[0]->device) return fail(SKB_EINVAL, "KDEs of one group must share a device");
+        for (int j = 0; j < k; j++)
+            if (kdes[j] == kdes[k]) return fail(SKB_EINVAL, "a KDE handle may appear once per group");
+        if (sign[k] != 1 && sign[k] != -1) return fail(SKB_EINVAL, "sign[%d] must be +1 or -1", k);
+    }
+    if (M == 0) return SKB_OK;
+    skb_kde* h0 = kdes[0];
+    DeviceGuard guard(h0->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t esz = q_dtype == SKB_F32 ? 4 : 8;
+    const bool q_dev = is_device_ptr(q);
+    const bool u_dev = !u || is_device_ptr(u);
+    const bool lp_dev = !out_logp || is_device_ptr(out_logp);
+    const bool lr_dev = !out_log_ratio || is_device_ptr(out_log_ratio);
+    const bool ac_dev = !accept || is_device_ptr(accept);
+    const bool ib_dev = !in_band || is_device_ptr(in_band);
+    const bool all_dev = q_dev && u_dev && lp_dev && lr_dev && ac_dev && ib_dev;
+    const int64_t step = all_dev ? M : STAGE_ROWS;
+    for (int64_t a = 0; a < M; a += step) {
+        const int64_t m = (M - a < step) ? (M - a) : step;
+        const void* qd = reinterpret_cast<const char*>(q) + (size_t)a * ldq * esz;
+        if (!q_dev) {
+            const size_t bytes = (size_t)m * ldq * esz;
+            SKB_CUDA(h0->q_stage.reserve(bytes));
+            SKB_CUDA(cudaMemcpyAsync(h0->q_stage.p, qd, bytes, cudaMemcpyHostToDevice, st));
+            qd = h0->q_stage.p;
+        }
+        GroupSpec g;
+        g.ratio = 1; g.sign = sign; g.log_abs_jac = log_abs_jac; g.log_m = log_m; g.band = band;
+        // aux staging: [u | log_ratio | logp x n_kde] doubles
+        const size_t aux_doubles = (size_t)m * (2 + (size_t)n_kde);
+        if (!(u_dev && lp_dev && lr_dev)) SKB_CUDA(h0->aux_stage.reserve(aux_doubles * 8));
+        double* aux = reinterpret_cast<double*>(h0->aux_stage.p);
+        if (u) {
+            if (u_dev) g.u = u + a;
+            else { SKB_CUDA(cudaMemcpyAsync(aux, u + a, (size_t)m * 8, cudaMemcpyHostToDevice, st)); g.u = aux; }
+        }
+        if (out_log_ratio) g.out_log_ratio = lr_dev ? out_log_ratio + a : aux + m;
+        if (!(ac_dev && ib_dev)) SKB_CUDA(h0->flag_stage.reserve((size_t)m * 2));
+        unsigned char* fl = reinterpret_cast<unsigned char*>(h0->flag_stage.p);
+        if (accept) g.accept = ac_dev ? accept + a : fl;
+        if (in_band) g.in_band = ib_dev ? in_band + a : fl + m;
+        DevJob dj[SKB_MAX_GROUP];
+        for (int k = 0; k < n_kde; k++) {
+            double* lp = nullptr;
+            if (out_logp) lp = lp_dev ? out_logp + (size_t)k * M + a : aux + (size_t)(2 + k) * m;
+            dj[k] = DevJob{kdes[k], qd, q_dtype == SKB_F32, 0, m, ldq, cols ? cols + (size_t)k * SKB_MAXD : nullptr,
+                           lp, nullptr, nullptr};
+        }
+        int rc = run_jobs_device(dj, n_kde, true, g, st);
+        if (rc) return rc;
+        if (!all_dev) {
+            if (out_log_ratio && !lr_dev)
+                SKB_CUDA(cudaMemcpyAsync(out_log_ratio + a, aux + m, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+            if (out_logp && !lp_dev)
+                for (int k = 0; k < n_kde; k++)
+                    SKB_CUDA(cudaMemcpyAsync(out_logp + (size_t)k * M + a, aux + (size_t)(2 + k) * m, (size_t)m * 8,
+                                             cudaMemcpyDeviceToHost, st));
+            if (accept && !ac_dev) SKB_CUDA(cudaMemcpyAsync(accept + a, fl, (size_t)m, cudaMemcpyDeviceToHost, st));
+            if (in_band && !ib_dev) SKB_CUDA(cudaMemcpyAsync(in_band + a, fl + m, (size_t)m, cudaMemcpyDeviceToHost, st));
+            SKB_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+    return SKB_OK;
+}
+
+// ---- draws ----------------------------------------------------------------------------------------
+int skb_draw(skb_handle h, int64_t M, const double* u, const double* z, uint64_t seed, uint64_t offset,
+             const int64_t* rows, int rcol, double rmin, double rmax, int max_attempts, int64_t* out_idx,
+             double* out_x, int64_t ld_out, double* out_z, uint8_t* out_flag, int64_t* n_flagged, void* stream)
+{
+    if (!h) return fail(SKB_EINVAL, "NULL handle");
+    if (M < 0) return fail(SKB_EINVAL, "negative draw count");
+    if ((u == nullptr) != (z == nullptr)) return fail(SKB_EINVAL, "u and z streams must be given together");
+    if (rcol >= h->hk.D) return fail(SKB_EINVAL, "window column %d out of range", rcol);
+    if (out_x && ld_out < h->hk.D) return fail(SKB_EINVAL, "ld_out < d");
+    if (n_flagged) *n_flagged = 0;
+    if (M == 0) return SKB_OK;
+    DeviceGuard guard(h->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int D = h->hk.D;
+    // All-or-nothing residency: either every buffer is on the device, or everything is staged.
+    const void* ptrs[] = {u, z, rows, out_idx, out_x, out_z, out_flag};
+    bool any_host = false, any_dev = false;
+    for (const void* p : ptrs) if (p) { if (is_device_ptr(p)) any_dev = true; else any_host = true; }
+    if (any_host && any_dev) return fail(SKB_EINVAL, "skb_draw: mix of host and device buffers is not supported");
+    unsigned long long* d_count = reinterpret_cast<unsigned long long*>(h->small.p);
+    if (n_flagged) SKB_CUDA(cudaMemsetAsync(d_count, 0, 8, st));
+    if (!any_host) {
+        SKB_CUDA(launch_draw(h->dk, D, M, u, z, seed, offset, reinterpret_cast<const long long*>(rows), rcol, rmin,
+                             rmax, max_attempts, reinterpret_cast<long long*>(out_idx), out_x, ld_out, out_z, out_flag,
+                             n_flagged ? d_count : nullptr, st));
+    } else {
+        if (rows && (out_x || out_z || out_idx || out_flag)) {
+            // scattered destination rows with host outputs: the caller owns the full arrays, so stage the
+            // draws densely and scatter on the host.
+        }
+        for (int64_t a = 0; a < M; a += STAGE_ROWS) {
+            const int64_t m = (M - a < STAGE_ROWS) ? (M - a) : STAGE_ROWS;
+            // layout of the staging block (doubles): u[m] z[m*D] x[m*D] zz[m*D] idx[m] then flags
+            const size_t nd = (size_t)m * (2 + 3 * (size_t)D);
+            SKB_CUDA(h->aux_stage.reserve(nd * 8 + (size_t)m));
+            double* base = reinterpret_cast<double*>(h->aux_stage.p);
+            double* du = base; double* dz = du + m; double* dx = dz + (size_t)m * D; double* dzz = dx + (size_t)m * D;
+            long long* didx = reinterpret_cast<long long*>(dzz + (size_t)m * D);
+            unsigned char* dfl = reinterpret_cast<unsigned char*>(didx + m);
+            if (u) {
+                SKB_CUDA(cudaMemcpyAsync(du, u + a, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+                SKB_CUDA(cudaMemcpyAsync(dz, z + (size_t)a * D, (size_t)m * D * 8, cudaMemcpyHostToDevice, st));
+            }
+            SKB_CUDA(launch_draw(h->dk, D, m, u ? du : nullptr, u ? dz : nullptr, seed, offset + (uint64_t)a, nullptr,
+                                 rcol, rmin, rmax, max_attempts, out_idx ? didx : nullptr, out_x ? dx : nullptr, D,
+                                 out_z ? dzz : nullptr, out_flag ? dfl : nullptr, n_flagged ? d_count : nullptr, st));
+            if (!rows) {
+                if (out_idx) SKB_CUDA(cudaMemcpyAsync(out_idx + a, didx, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+                if (out_z) SKB_CUDA(cudaMemcpyAsync(out_z + (size_t)a * D, dzz, (size_t)m * D * 8, cudaMemcpyDeviceToHost, st));
+                if (out_flag) SKB_CUDA(cudaMemcpyAsync(out_flag + a, dfl, (size_t)m, cudaMemcpyDeviceToHost, st));
+                if (out_x) {
+                    if (ld_out == D) SKB_CUDA(cudaMemcpyAsync(out_x + (size_t)a * D, dx, (size_t)m * D * 8, cudaMemcpyDeviceToHost, st));
+                    else SKB_CUDA(cudaMemcpy2DAsync(out_x + (size_t)a * ld_out, (size_t)ld_out * 8, dx, (size_t)D * 8,
+                                                    (size_t)D * 8, (size_t)m, cudaMemcpyDeviceToHost, st));
+                }
+                SKB_CUDA(cudaStreamSynchronize(st));
+            } else {
+                std::vector<double> hx, hz;
+                std::vector<long long> hi;
+                std::vector<unsigned char> hf;
+                if (out_x) { hx.resize((size_t)m * D); SKB_CUDA(cudaMemcpyAsync(hx.data(), dx, (size_t)m * D * 8, cudaMemcpyDeviceToHost, st)); }
+                if (out_z) { hz.resize((size_t)m * D); SKB_CUDA(cudaMemcpyAsync(hz.data(), dzz, (size_t)m * D * 8, cudaMemcpyDeviceToHost, st)); }
+                if (out_idx) { hi.resize((size_t)m); SKB_CUDA(cudaMemcpyAsync(hi.data(), didx, (size_t)m * 8, cudaMemcpyDeviceToHost, st)); }
+                if (out_flag) { hf.resize((size_t)m); SKB_CUDA(cudaMemcpyAsync(hf.data(), dfl, (size_t)m, cudaMemcpyDeviceToHost, st)); }
+                SKB_CUDA(cudaStreamSynchronize(st));
+                for (int64_t i = 0; i < m; i++) {
+                    const int64_t o = rows[a + i];
+                    if (out_x) memcpy(out_x + (size_t)o * ld_out, &hx[(size_t)i * D], (size_t)D * 8);
+                    if (out_z) memcpy(out_z + (size_t)o * D, &hz[(size_t)i * D], (size_t)D * 8);
+                    if (out_idx) out_idx[o] = hi[(size_t)i];
+                    if (out_flag) out_flag[o] = hf[(size_t)i];
+                }
+            }
+        }
+    }
+    if (n_flagged) {
+        unsigned long long c = 0;
+        SKB_CUDA(cudaMemcpyAsync(&c, d_count, 8, cudaMemcpyDeviceToHost, st));
+        SKB_CUDA(cudaStreamSynchronize(st));
+        *n_flagged = (int64_t)c;
+    }
+    return SKB_OK;
+}
+
+// ---- compaction -----------------------------------------------------------------------------------
+int skb_compact(const uint8_t* flags, int64_t M, const void* rows, int dtype, int64_t ld, void* out,
+                int64_t* out_index, int64_t* n_out, void* stream)
+{
+    if (M < 0) return fail(SKB_EINVAL, "negative row count");
+    if (n_out) *n_out = 0;
+    if (M == 0) return SKB_OK;
+    if (!flags) return fail(SKB_EINVAL, "NULL flags");
+    if (dtype != SKB_F64 && dtype != SKB_F32) return fail(SKB_EINVAL, "bad dtype %d", dtype);
+    if ((rows == nullptr) != (out == nullptr)) return fail(SKB_EINVAL, "rows and out must be given together");
+    if (rows && ld < 1) return fail(SKB_EINVAL, "bad row stride");
+    const void* ptrs[] = {flags, rows, out, out_index};
+    for (const void* p : ptrs)
+        if (p && !is_device_ptr(p)) return fail(SKB_EINVAL, "skb_compact works on device buffers only");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long nb = compact_nblocks(M);
+    unsigned long long* ws = nullptr;
+    SKB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), (size_t)(nb + 1) * 8, st));
+    cudaError_t e = launch_compact(flags, M, rows, dtype == SKB_F32 ? 4 : 8, ld, out,
+                                   reinterpret_cast<long long*>(out_index), ws, ws + nb, st);
+    if (e == cudaSuccess && n_out) {
+        unsigned long long c = 0;
+        e = cudaMemcpyAsync(&c, ws + nb, 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        *n_out = (int64_t)c;
+    }
+    cudaFreeAsync(ws, st);
+    SKB_CUDA(e);
+    return SKB_OK;
+}
+
+int skb_debug_counters(int device, uint64_t* out4, int reset)
+{
+    if (!out4) return fail(SKB_EINVAL, "NULL output pointer");
+    if (skb_device_count() <= 0) return fail(SKB_ECUDA, "no CUDA device available");
+    DeviceGuard guard(device);
+    unsigned long long tmp[4];
+    SKB_CUDA(cudaDeviceSynchronize());
+    SKB_CUDA(read_stats(tmp, reset));
+    for (int i = 0; i < 4; i++) out4[i] = tmp[i];
+    return SKB_OK;
+}
+
+int skb_measure_pipes(int device, double ms_each, double* fma_lane_per_s, double* ex2_per_s)
+{
+    if (!fma_lane_per_s || !ex2_per_s) return fail(SKB_EINVAL, "NULL output pointer");
+    int ndev = skb_device_count();
+    if (ndev <= 0) return fail(SKB_ECUDA, "no CUDA device available");
+    if (device < 0 || device >= ndev) return fail(SKB_EINVAL, "device %d out of range", device);
+    DeviceGuard guard(device);
+    SKB_CUDA(measure_pipes(ms_each > 0 ? ms_each : 50.0, fma_lane_per_s, ex2_per_s));
+    return SKB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,110 @@
+// Internal declarations shared by the sm_100a kernels and the C-ABI glue (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/skb.h"
+
+namespace skb {
+
+typedef unsigned long long u64;
+
+// ---- training-tile geometry -------------------------------------------------------------------
+// The fitted KDE lives in HBM as tiles of TN points in SoA order: tile t is one contiguous block
+//   [D+1][TN] fp32 = D rows of prescaled whitened coordinates + 1 row of normalised weights,
+// so that ONE 1-D TMA bulk copy (cp.async.bulk, SASS UBLKCP) moves a whole tile into shared memory
+// and an LDS.128 of row k yields two packed {x_j, x_j+1} operands for FADD2/FFMA2.
+constexpr int TN = 256;              // training points per tile
+constexpr int NSTAGE = 4;            // TMA ring depth
+constexpr int NT = 128;              // threads per CTA of the score kernel
+constexpr int FB = 256;              // queries per finalize block (arrival-counter granularity)
+constexpr float PAD_COORD = 1.0e18f; // coordinate of padding / zero-weight points: exp2(-1e36) == 0
+
+__host__ __device__ constexpr int queries_per_thread(int D) { return D <= 4 ? 8 : (D <= 8 ? 4 : 2); }
+__host__ __device__ constexpr int stage_floats(int D) { return (D + 1) * TN; }
+
+// Device-resident description of one fitted KDE (one per handle, uploaded at skb_create).
+struct KdeDev {
+    const float* tiles;      // [ntiles][D+1][TN]
+    const double* zt64;      // [N][D] whitened fp64 rows (draw centres)
+    const double* cumsum_w;  // [N] sequential fp64 cumsum (NULL for unweighted)
+    long long N;
+    int ntiles;
+    int D;
+    int has_w;
+    int has_winv;
+    double c;                // prescale sqrt(log2(e)/2)/h : exp(-d^2/2h^2) == exp2(-|c dz|^2)
+    double h;
+    double sum_w;
+    double log_norm;         // log_knorm - log(sum_w) + log(w_max)   (natural log)
+    double mu[SKB_MAXD];
+    double Wc[SKB_MAXD * SKB_MAXD];    // forward map prescaled by c:  c*z_k = sum_i (x_i-mu_i) Wc[i*D+k]
+    double Winv[SKB_MAXD * SKB_MAXD];  // inverse map: x_i = sum_k z_k Winv[k*D+i] + mu_i
+};
+
+// One (KDE, query table) job of a score launch; blockIdx.y indexes these.
+struct ScoreJob {
+    const KdeDev* kde;
+    const void* q;
+    long long M;
+    long long ldq;
+    int q_f32;
+    int q_is_whitened;
+    int cols_identity;       // cols == 0..D-1 and rows are dense & 16B aligned -> vector loads
+    int nsplit;              // training-set splits (blockIdx.z)
+    int fin_first, fin_count;  // finalize group = jobs [fin_first, fin_first+fin_count) of FinTable
+    int* counters;           // [ceil(M/FB)] arrival counters of the group (NULL -> finalize from registers)
+    int expected;            // arrivals per finalize block
+    int fin_slot;            // this job's index in the FinTable
+    signed char cols[SKB_MAXD];
+};
+
+struct FinJob {
+    double2* partial;        // [nsplit][M]  (m, S):  sum_j w_j exp2(-acc_j) = S * exp2(-m)
+    double* out_logp;        // [M] natural log density, or NULL
+    double* out_m;           // partial-mode outputs (natural-log m, s) or NULL
+    double* out_s;
+    double log_norm;
+    double sign_logjac;      // sign * log|jac|
+    int nsplit;
+    int sign;
+};
+
+struct FinTable {
+    FinJob fj[SKB_MAX_JOBS];
+    // ratio / accept part (group mode)
+    const double* u;         // [M] uniforms or NULL
+    double log_m;
+    double band;
+    double* out_log_ratio;
+    unsigned char* accept;
+    unsigned char* in_band;
+    int ratio;               // 1 -> form the ratio over the group
+};
+
+struct ScoreLaunch {
+    ScoreJob jobs[SKB_MAX_JOBS];
+    FinTable fin;
+};
+
+// kernels / launchers (defined in the .cu files)
+cudaError_t launch_pack(const void* train, int f32, long long N, int D, long long ld, int is_whitened,
+                        const KdeDev* kde_dev, const double* w, double inv_wmax,
+                        float* tiles, double* zt64, int ntiles, cudaStream_t st);
+cudaError_t launch_score(int D, const ScoreLaunch& L, int njobs, long long max_qblocks, int max_split,
+                         cudaStream_t st);
+cudaError_t launch_draw(const KdeDev* kde, int D, long long M, const double* u, const double* z,
+                        uint64_t seed, uint64_t offset, const long long* rows,
+                        int rcol, double rmin, double rmax, int max_attempts,
+                        long long* out_idx, double* out_x, long long ld_out, double* out_z,
+                        unsigned char* out_flag, unsigned long long* n_flagged, cudaStream_t st);
+cudaError_t launch_compact(const unsigned char* flags, long long M, const void* rows, int elem_bytes,
+                           long long ld, void* out, long long* out_index,
+                           unsigned long long* block_counts, unsigned long long* total,
+                           cudaStream_t st);
+long long compact_nblocks(long long M);
+cudaError_t read_stats(unsigned long long* out4, int reset);
+cudaError_t measure_pipes(double ms_each, double* fma_lane_per_s, double* ex2_per_s);
+
+void count_launch(int n = 1);
+
+}  // namespace skb

@@ -1,0 +1,577 @@
+// Gaussian-KDE log-density scoring for sm_100a (B200): the replacement for sklearn's KD-tree
+// `kernel_density` walk (sklearn neighbors/_binary_tree.pxi.tp:1393-1535, 2149-2290) that
+// skysampler's KDEContainer.score_samples reaches (skysampler/emulator.py:380-385).
+//
+// Every (query, training point) pair is evaluated — no tree, no tolerance:
+//     log p(z) = log_norm + log sum_j w_j exp(-|z - z_j|^2 / 2h^2)
+// with fp32 pair terms and an fp64 log-sum-exp state per query.
+//
+// Per pair the FMA pipe sees exactly 2D+1 lane operations (D subtractions, D fused squares, one
+// weighted accumulate) and the SFU one EX2:
+//   * coordinates are prescaled by c = sqrt(log2(e)/2)/h so that exp(-d^2/2h^2) = exp2(-|c dz|^2);
+//   * the per-query reference exponent m is folded into the accumulator seed (acc starts at -m),
+//     so no per-pair shift is needed; m only has to lie in a ~216-binade window around the true
+//     minimum distance.  It is seeded by a min-only pass over the first tile of a split and
+//     corrected lazily: a 64-point block whose fp32 partial sum overflows is re-run after a
+//     min-only pass over that block (rare);
+//   * the weight is applied as sum = fma(w_j, e, sum) — same cost as an add;
+//   * two training points ride in one FADD2/FFMA2 (packed fp32x2, one issue slot for two lane
+//     ops), which leaves issue slots for MUFU.EX2 and LDS — measured on B200: 8xFFMA2 + 2xMUFU
+//     per loop co-issue at 98% of the FMA peak, the scalar form is issue-bound at 80%.
+// Training tiles arrive in shared memory through a 4-deep ring of 1-D TMA bulk copies
+// (cp.async.bulk + mbarrier complete_tx); all lanes of a warp read the same tile words
+// (LDS.128 broadcast), each thread owning Q whole queries, so no cross-lane reduction exists.
+#include "skb_internal.h"
+#include <math.h>
+
+namespace skb {
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 pk(float lo, float hi) {
+    u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void upk(u64 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+    u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
+}
+__device__ __forceinline__ float ex2_neg(float a) {   // 2^(-a), MUFU.EX2 with the negate modifier
+    float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-a)); return r;
+}
+__device__ __forceinline__ float min3(float a, float b, float c) {
+    float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra D_%=;\n\t"
+        "bra W_%=;\n"
+        "D_%=:\n\t}"
+        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// diagnostics: [0] overflow re-runs of a 64-point block (warp level), [1] blocks processed (warp level)
+__device__ unsigned long long g_stats[4];
+
+constexpr float OVERFLOW_LIMIT = 1.329228e36f;    // 2^120: a block partial sum at/above this is re-run
+constexpr float REF_BIAS = 90.f;                  // reference sits this many binades below the closest point seen
+constexpr int SUB = 64;                           // points per overflow-checked block
+
+// ---------------------------------------------------------------------------------------------
+// One pass of a thread's Q queries over (part of) a shared-memory tile.
+//   MIN_ONLY = false:  sum2[q] += w_j * 2^(m_q - acc_j)      (packed halves = even / odd points)
+//   MIN_ONLY = true :  amin[q]  = min(amin[q], acc_j - m_q)  (no SFU work)
+// ---------------------------------------------------------------------------------------------
+template <int D, int Q, bool MIN_ONLY>
+__device__ __forceinline__ void tile_pass(const float* __restrict__ tile, int npts,
+                                          const u64 (&q2)[Q][D], const u64 (&nm2)[Q],
+                                          u64 (&sum2)[Q], float (&amin)[Q])
+{
+#pragma unroll 1
+    for (int j = 0; j < npts; j += 4) {
+        u64 xa[D], xb[D];
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            const float4 v = *reinterpret_cast<const float4*>(tile + k * TN + j);
+            xa[k] = pk(v.x, v.y);
+            xb[k] = pk(v.z, v.w);
+        }
+        u64 wa = 0, wb = 0;
+        if (!MIN_ONLY) {
+            const float4 w4 = *reinterpret_cast<const float4*>(tile + D * TN + j);
+            wa = pk(w4.x, w4.y);
+            wb = pk(w4.z, w4.w);
+        }
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            u64 aa = nm2[q], ab = nm2[q];
+#pragma unroll
+            for (int k = 0; k < D; k++) {
+                const u64 da = sub2(q2[q][k], xa[k]);
+                const u64 db = sub2(q2[q][k], xb[k]);
+                aa = fma2(da, da, aa);
+                ab = fma2(db, db, ab);
+            }
+            float a0, a1, b0, b1;
+            upk(aa, a0, a1);
+            upk(ab, b0, b1);
+            if (MIN_ONLY) {
+                amin[q] = min3(amin[q], a0, a1);
+                amin[q] = min3(amin[q], b0, b1);
+            } else {
+                const u64 ea = pk(ex2_neg(a0), ex2_neg(a1));
+                const u64 eb = pk(ex2_neg(b0), ex2_neg(b1));
+                sum2[q] = fma2(wa, ea, sum2[q]);
+                sum2[q] = fma2(wb, eb, sum2[q]);
+            }
+        }
+    }
+}
+
+// log p (natural) of query r from the per-split partials of one job.
+__device__ __forceinline__ void merge_partials(const double2* __restrict__ partial, int nsplit,
+                                               long long M, long long r, double& mstar, double& S)
+{
+    mstar = INFINITY;
+    bool nan_in = false;
+    for (int s = 0; s < nsplit; s++) {
+        const double2 p = partial[(long long)s * M + r];
+        if (p.y > 0.0) mstar = fmin(mstar, p.x);          // weightless splits (S == 0) carry no reference
+        nan_in |= (p.y != p.y);
+    }
+    S = 0.0;
+    if (nan_in) { S = NAN; mstar = 0.0; return; }
+    if (!(mstar < INFINITY)) { mstar = 0.0; return; }
+    for (int s = 0; s < nsplit; s++) {
+        const double2 p = partial[(long long)s * M + r];
+        if (!(p.y > 0.0)) continue;
+        double e = mstar - p.x;                 // <= 0, integer valued
+        if (!(e > -4000.0)) e = -4000.0;
+        S += ldexp(p.y, (int)e);
+    }
+}
+
+constexpr double LN2 = 0.693147180559945309417232121458;
+
+__device__ __forceinline__ void finalize_query(const FinTable& fin, int first, int count,
+                                               long long M, long long r)
+{
+    double log_ratio = -fin.log_m;
+    for (int f = first; f < first + count; f++) {
+        const FinJob& fj = fin.fj[f];
+        double mstar, S;
+        merge_partials(fj.partial, fj.nsplit, M, r, mstar, S);
+        if (fj.out_m) { fj.out_m[r] = -mstar * LN2; fj.out_s[r] = S; }
+        const double lp = fj.log_norm + log(S) - mstar * LN2;
+        if (fj.out_logp) fj.out_logp[r] = lp;
+        log_ratio += fj.sign * lp + fj.sign_logjac;
+    }
+    if (fin.ratio) {
+        if (fin.out_log_ratio) fin.out_log_ratio[r] = log_ratio;
+        if (fin.u) {
+            const double lu = log(fin.u[r]);
+            if (fin.accept) fin.accept[r] = (lu < log_ratio) ? 1 : 0;
+            if (fin.in_band) fin.in_band[r] = (fabs(log_ratio - lu) <= fin.band) ? 1 : 0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The score kernel.  grid = (query blocks, jobs, training splits), block = NT threads.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(NT)
+skb_score_kernel(const __grid_constant__ ScoreLaunch L)
+{
+    constexpr int Q = queries_per_thread(D);
+    constexpr int QB = NT * Q;
+    constexpr int STAGE_FLOATS = stage_floats(D);
+    constexpr uint32_t STAGE_BYTES = STAGE_FLOATS * sizeof(float);
+    constexpr int NWARP = NT / 32;
+
+    const ScoreJob& job = L.jobs[blockIdx.y];
+    const long long M = job.M;
+    const long long qbase = (long long)blockIdx.x * QB;
+    if (qbase >= M || (int)blockIdx.z >= job.nsplit) return;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* stages = reinterpret_cast<float*>(smem_raw);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NSTAGE * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + NSTAGE;
+    __shared__ int s_last[QB / FB];
+
+    const int tid = threadIdx.x;
+    const KdeDev* __restrict__ kde = job.kde;
+    const int ntiles = kde->ntiles;
+    const int nsplit = job.nsplit;
+    const int t0 = (int)(((long long)ntiles * blockIdx.z) / nsplit);
+    const int t1 = (int)(((long long)ntiles * (blockIdx.z + 1)) / nsplit);
+    const int ntl = t1 - t0;
+    const float* __restrict__ gtiles = kde->tiles + (size_t)t0 * STAGE_FLOATS;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NWARP); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int npre = ntl < NSTAGE ? ntl : NSTAGE;
+        for (int s = 0; s < npre; s++) {
+            mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+            tma_bulk_g2s(stages + (size_t)s * STAGE_FLOATS, gtiles + (size_t)s * STAGE_FLOATS, STAGE_BYTES,
+                         &full_bar[s]);
+        }
+    }
+
+    // ---- prologue: load this thread's Q query rows, whiten + prescale in fp64, pack as {z, z} ----
+    u64 q2[Q][D];
+    {
+        const double c = kde->c;
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            long long r = qbase + (long long)q * NT + tid;
+            if (r >= M) r = M - 1;                      // clamp: duplicates are computed, never stored
+            double x[D];
+            if (job.q_f32) {
+                const float* row = reinterpret_cast<const float*>(job.q) + r * job.ldq;
+                if (job.cols_identity && (D % 4 == 0)) {
+#pragma unroll
+                    for (int i = 0; i < D; i += 4) {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(row + i));
+                        x[i] = v.x; x[i + 1] = v.y; x[i + 2] = v.z; x[i + 3] = v.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < D; i++) x[i] = __ldg(row + job.cols[i]);
+                }
+            } else {
+                const double* row = reinterpret_cast<const double*>(job.q) + r * job.ldq;
+                if (job.cols_identity && (D % 2 == 0)) {
+#pragma unroll
+                    for (int i = 0; i < D; i += 2) {
+                        const double2 v = __ldg(reinterpret_cast<const double2*>(row + i));
+                        x[i] = v.x; x[i + 1] = v.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < D; i++) x[i] = __ldg(row + job.cols[i]);
+                }
+            }
+            if (job.q_is_whitened) {
+#pragma unroll
+                for (int k = 0; k < D; k++) { const float z = (float)(x[k] * c); q2[q][k] = pk(z, z); }
+            } else {
+#pragma unroll
+                for (int i = 0; i < D; i++) x[i] -= kde->mu[i];
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    double z = 0.0;
+#pragma unroll
+                    for (int i = 0; i < D; i++) z = fma(x[i], kde->Wc[i * D + k], z);
+                    const float zf = (float)z;
+                    q2[q][k] = pk(zf, zf);
+                }
+            }
+        }
+    }
+
+    // ---- main loop over this split's tiles -----------------------------------------------------
+    // Reference exponent window.  Pair terms are t = 2^(mref - acc) in fp32 (flush below 2^-126,
+    // overflow above 2^127).  The log-sum is carried by terms within ~30 binades of the closest
+    // point, so any mref in (acc_min - 96, acc_min + 120) is exact to fp32 rounding.  mref is set to
+    // (smallest acc seen) - REF_BIAS: points up to ~210 binades closer than anything seen so far are
+    // absorbed without action; beyond that the SUB-point block overflows and is re-run once.
+    float mref[Q];          // integer-valued reference exponent per query
+    double S[Q];            // fp64 running sum at reference mref:  sum_j w_j 2^(-acc_j) = S * 2^(-mref)
+    u64 nm2[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) { mref[q] = 0.f; S[q] = 0.0; nm2[q] = pk(0.f, 0.f); }
+
+    const int lane = tid & 31;
+    unsigned n_rerun = 0, n_blocks = 0;
+    const int pilot_points = ntl >= 32 ? TN : 64;
+    bool have_ref = false;
+    for (int it = 0; it < ntl; it++) {
+        const int s = it % NSTAGE;
+        const uint32_t ph = (it / NSTAGE) & 1;
+        // producer: once every warp has released the stage of the previous tile, refill it
+        if (tid == 0 && it >= 1 && it - 1 + NSTAGE < ntl) {
+            const int sp = (it - 1) % NSTAGE;
+            mbar_wait(&empty_bar[sp], ((it - 1) / NSTAGE) & 1);
+            mbar_expect_tx(&full_bar[sp], STAGE_BYTES);
+            tma_bulk_g2s(stages + (size_t)sp * STAGE_FLOATS, gtiles + (size_t)(it - 1 + NSTAGE) * STAGE_FLOATS,
+                         STAGE_BYTES, &full_bar[sp]);
+        }
+        __syncwarp();
+        mbar_wait(&full_bar[s], ph);
+        const float* tile = stages + (size_t)s * STAGE_FLOATS;
+
+        u64 sum2[Q];
+        float amin[Q];
+        if (!have_ref) {
+            // pilot: a min-only pass fixes the first reference exponent of each query.  Padding /
+            // zero-weight points sit at PAD_COORD, so a range holding only those is recognised by its
+            // (query independent) huge minimum and skipped.
+#pragma unroll
+            for (int q = 0; q < Q; q++) amin[q] = INFINITY;
+            tile_pass<D, Q, true>(tile, pilot_points, q2, nm2, sum2, amin);
+            bool only_pad = true;
+#pragma unroll
+            for (int q = 0; q < Q; q++) only_pad &= !(amin[q] < 1.0e30f);
+            if (pilot_points < TN && __all_sync(0xffffffffu, only_pad)) {
+                tile_pass<D, Q, true>(tile, TN, q2, nm2, sum2, amin);
+                only_pad = true;
+#pragma unroll
+                for (int q = 0; q < Q; q++) only_pad &= !(amin[q] < 1.0e30f);
+            }
+            if (__all_sync(0xffffffffu, only_pad)) {     // the whole tile carries no weight
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[s]);
+                continue;
+            }
+            have_ref = true;
+#pragma unroll
+            for (int q = 0; q < Q; q++) {
+                float m = floorf(amin[q]) - REF_BIAS;
+                if (!(fabsf(m) < 1.0e30f)) m = 0.f;      // inf/NaN rows: keep a finite reference
+                mref[q] = m;
+                nm2[q] = pk(-m, -m);
+            }
+        }
+#pragma unroll 1
+        for (int sub = 0; sub < TN; sub += SUB) {
+            const float* blk = tile + sub;
+            n_blocks++;
+            for (;;) {
+#pragma unroll
+                for (int q = 0; q < Q; q++) sum2[q] = pk(0.f, 0.f);
+                tile_pass<D, Q, false>(blk, SUB, q2, nm2, sum2, amin);
+                bool bad = false;
+                float ts[Q];
+#pragma unroll
+                for (int q = 0; q < Q; q++) {
+                    float lo, hi; upk(sum2[q], lo, hi);
+                    ts[q] = lo + hi;
+                    bad |= !(ts[q] < OVERFLOW_LIMIT);
+                }
+                if (!__any_sync(0xffffffffu, bad)) {
+#pragma unroll
+                    for (int q = 0; q < Q; q++) S[q] += (double)ts[q];
+                    break;
+                }
+                // rare: a query met a point far closer than its window allows -> recentre, re-run block
+                n_rerun++;
+#pragma unroll
+                for (int q = 0; q < Q; q++) amin[q] = INFINITY;
+                tile_pass<D, Q, true>(blk, SUB, q2, nm2, sum2, amin);
+                bool fixable = false;
+#pragma unroll
+                for (int q = 0; q < Q; q++) {
+                    if (!(ts[q] < OVERFLOW_LIMIT)) {
+                        const float delta = floorf(amin[q]) - REF_BIAS;   // new reference relative to mref
+                        if (delta < 0.f && delta > -1.0e30f) {
+                            fixable = true;
+                            mref[q] += delta;
+                            nm2[q] = pk(-mref[q], -mref[q]);
+                            double e = (double)delta;
+                            if (e < -4000.0) e = -4000.0;
+                            S[q] = ldexp(S[q], (int)e);
+                        } else {
+                            ts[q] = NAN;                             // NaN/inf input row: propagate
+                        }
+                    }
+                }
+                if (!__any_sync(0xffffffffu, fixable)) {
+#pragma unroll
+                    for (int q = 0; q < Q; q++) S[q] += (double)ts[q];
+                    break;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+
+    if (lane == 0) {
+        if (n_rerun) atomicAdd(&g_stats[0], (unsigned long long)n_rerun);
+        atomicAdd(&g_stats[1], (unsigned long long)n_blocks);
+    }
+
+    // ---- epilogue ------------------------------------------------------------------------------
+    const FinJob& myfin = L.fin.fj[job.fin_slot];
+    if (job.counters == nullptr) {
+        // single split, ungrouped: finalize straight from registers
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const long long r = qbase + (long long)q * NT + tid;
+            if (r < M) {
+                if (myfin.out_m) { myfin.out_m[r] = -(double)mref[q] * LN2; myfin.out_s[r] = S[q]; }
+                if (myfin.out_logp) myfin.out_logp[r] = myfin.log_norm + log(S[q]) - (double)mref[q] * LN2;
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        const long long r = qbase + (long long)q * NT + tid;
+        if (r < M) myfin.partial[(long long)blockIdx.z * M + r] = make_double2((double)mref[q], S[q]);
+    }
+    // last-arriving CTA of each finalize block (FB queries) merges splits / forms the ratio + accept
+    __threadfence();
+    __syncthreads();
+    if (tid < QB / FB) {
+        const long long fb = qbase / FB + tid;
+        int last = 0;
+        if (fb * FB < M) {
+            const int prev = atomicAdd(&job.counters[fb], 1);
+            last = (prev == job.expected - 1);
+            if (last) job.counters[fb] = 0;             // self-reset for the next call
+        }
+        s_last[tid] = last;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int b = 0; b < QB / FB; b++) {
+        if (!s_last[b]) continue;
+        __threadfence();
+        for (int i = tid; i < FB; i += NT) {
+            const long long r = qbase + (long long)b * FB + i;
+            if (r < M) finalize_query(L.fin, job.fin_first, job.fin_count, M, r);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tile packing (skb_create): whiten (if raw), prescale, cast, transpose into [tile][D+1][TN].
+// ---------------------------------------------------------------------------------------------
+__global__ void skb_pack_kernel(const void* __restrict__ train, int f32, long long N, int D, long long ld,
+                                int is_whitened, const KdeDev* __restrict__ kde,
+                                const double* __restrict__ w, double inv_wmax,
+                                float* __restrict__ tiles, double* __restrict__ zt64, int ntiles)
+{
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= (long long)ntiles * TN) return;
+    const long long t = j / TN;
+    const int o = (int)(j % TN);
+    float* dst = tiles + (size_t)t * (D + 1) * TN + o;
+    if (j >= N) {
+        for (int k = 0; k < D; k++) dst[k * TN] = PAD_COORD;
+        dst[D * TN] = 0.f;
+        return;
+    }
+    double x[SKB_MAXD], z[SKB_MAXD];
+    for (int i = 0; i < D; i++)
+        x[i] = f32 ? (double)reinterpret_cast<const float*>(train)[j * ld + i]
+                   : reinterpret_cast<const double*>(train)[j * ld + i];
+    if (is_whitened) {
+        for (int k = 0; k < D; k++) z[k] = x[k];
+    } else {
+        // z = (x - mu) . W  in fp64;  Wc = W * c  ->  z = ((x - mu) . Wc) / c
+        for (int i = 0; i < D; i++) x[i] -= kde->mu[i];
+        for (int k = 0; k < D; k++) {
+            double a = 0.0;
+            for (int i = 0; i < D; i++) a = fma(x[i], kde->Wc[i * D + k], a);
+            z[k] = a / kde->c;
+        }
+    }
+    for (int k = 0; k < D; k++) zt64[j * D + k] = z[k];
+    const double wj = w ? w[j] : 1.0;
+    if (wj > 0.0) {
+        for (int k = 0; k < D; k++) dst[k * TN] = (float)(z[k] * kde->c);
+        dst[D * TN] = (float)(wj * inv_wmax);
+    } else {
+        for (int k = 0; k < D; k++) dst[k * TN] = PAD_COORD;
+        dst[D * TN] = 0.f;
+    }
+}
+
+cudaError_t launch_pack(const void* train, int f32, long long N, int D, long long ld, int is_whitened,
+                        const KdeDev* kde_dev, const double* w, double inv_wmax,
+                        float* tiles, double* zt64, int ntiles, cudaStream_t st)
+{
+    const long long total = (long long)ntiles * TN;
+    const int bs = 256;
+    skb_pack_kernel<<<(unsigned)((total + bs - 1) / bs), bs, 0, st>>>(train, f32, N, D, ld, is_whitened, kde_dev,
+                                                                      w, inv_wmax, tiles, zt64, ntiles);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <int D>
+static cudaError_t launch_score_d(const ScoreLaunch& L, int njobs, long long max_qblocks, int max_split,
+                                  cudaStream_t st)
+{
+    const size_t smem = (size_t)NSTAGE * stage_floats(D) * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t);
+    cudaError_t e = cudaFuncSetAttribute(skb_score_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((unsigned)max_qblocks, (unsigned)njobs, (unsigned)max_split);
+    skb_score_kernel<D><<<grid, NT, smem, st>>>(L);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t read_stats(unsigned long long* out4, int reset)
+{
+    cudaError_t e = cudaMemcpyFromSymbol(out4, g_stats, sizeof(unsigned long long) * 4);
+    if (e == cudaSuccess && reset) {
+        unsigned long long z[4] = {0, 0, 0, 0};
+        e = cudaMemcpyToSymbol(g_stats, z, sizeof(z));
+    }
+    return e;
+}
+
+template <int D>
+static int occupancy_d()
+{
+    const size_t smem = (size_t)NSTAGE * stage_floats(D) * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t);
+    int n = 0;
+    if (cudaFuncSetAttribute(skb_score_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, skb_score_kernel<D>, NT, smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 2;
+    }
+    return n > 0 ? n : 1;
+}
+
+int score_ctas_per_sm(int D)
+{
+    static int cache[SKB_MAXD + 1] = {0};
+    if (D < 1 || D > SKB_MAXD) return 1;
+    if (cache[D] == 0) {
+        switch (D) {
+#define SKB_CASE(d) case d: cache[D] = occupancy_d<d>(); break;
+            SKB_CASE(1) SKB_CASE(2) SKB_CASE(3) SKB_CASE(4) SKB_CASE(5) SKB_CASE(6) SKB_CASE(7) SKB_CASE(8)
+            SKB_CASE(9) SKB_CASE(10) SKB_CASE(11) SKB_CASE(12) SKB_CASE(13) SKB_CASE(14) SKB_CASE(15) SKB_CASE(16)
+#undef SKB_CASE
+        }
+    }
+    return cache[D];
+}
+
+static_assert(sizeof(ScoreLaunch) <= 4000, "ScoreLaunch must fit the classic 4 KB kernel-parameter space");
+
+cudaError_t launch_score(int D, const ScoreLaunch& L, int njobs, long long max_qblocks, int max_split,
+                         cudaStream_t st)
+{
+    switch (D) {
+#define SKB_CASE(d) case d: return launch_score_d<d>(L, njobs, max_qblocks, max_split, st);
+        SKB_CASE(1) SKB_CASE(2) SKB_CASE(3) SKB_CASE(4) SKB_CASE(5) SKB_CASE(6) SKB_CASE(7) SKB_CASE(8)
+        SKB_CASE(9) SKB_CASE(10) SKB_CASE(11) SKB_CASE(12) SKB_CASE(13) SKB_CASE(14) SKB_CASE(15) SKB_CASE(16)
+#undef SKB_CASE
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace skb
