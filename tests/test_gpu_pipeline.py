@@ -1,0 +1,124 @@
+"""The callers of the path (emulator.py:525-748) on the B200 backend vs the reference's golden outputs."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import load_golden
+from oracle import accept as oaccept
+
+pytestmark = pytest.mark.gpu
+
+
+def _containers(g):
+    from skysampler_b200 import KDEContainer
+    seeds = [int(s) for s in g["seeds"]]
+    deep_c = {"container": KDEContainer(pd.DataFrame(g["deep_c"], columns=["C0", "C1", "C2"]), None, seed=seeds[0])}
+    deep_smc = {"container": KDEContainer(pd.DataFrame(g["deep_smc"], columns=["MAG", "C0", "C1", "C2"]), None, seed=seeds[1])}
+    wide_cr = {"container": KDEContainer(pd.DataFrame(g["wide_cr"], columns=["C0", "C1", "C2", "LOGR"]), pd.Series(g["w_cr"]), seed=seeds[2])}
+    wide_r = {"container": KDEContainer(pd.DataFrame(g["wide_r"], columns=["LOGR"]), pd.Series(g["w_r"]), seed=seeds[3])}
+    columns = {"cols_dc": ["C0", "C1", "C2"], "cols_wr": ["LOGR"], "cols_wcr": ["C0", "C1", "C2", "LOGR"]}
+    return wide_cr, wide_r, deep_c, deep_smc, columns
+
+
+def test_rejection_sampler_driver_slice_matches_reference():
+    """bin/delta_rejection_sampler_v01.py:95-110: make_naive_infodicts -> run_scores, same seeds."""
+    from skysampler_b200 import emulator
+    g = load_golden("driver_naive")
+    wide_cr, wide_r, deep_c, deep_smc, columns = _containers(g)
+    infodicts, samples = emulator.make_naive_infodicts(wide_cr, wide_r, deep_c, deep_smc, columns,
+                                                       nsamples=int(g["nsamples"]), nchunks=int(g["nchunks"]),
+                                                       bandwidth=float(g["bandwidth"]), rmin=None, rmax=float(g["rmax"]))
+    assert list(samples.columns) == [str(c) for c in g["sample_columns"]]
+    np.testing.assert_allclose(samples.values, g["samples_exact"], rtol=0, atol=1e-9)       # proposals replayed
+    assert len(infodicts) == 4 and sum(len(i["sample"]) for i in infodicts) == len(samples)
+    assert wide_r["container"].kde is None                                                  # dropped, picklable
+    result = emulator.run_scores(infodicts)
+    assert list(result.columns) == [str(c) for c in g["score_columns"]]
+    ref = pd.DataFrame(g["scores_exact"], columns=result.columns)
+    for col in ("dc_jac", "wr_jac", "wcr_jac"):
+        np.testing.assert_allclose(result[col].values, ref[col].values, rtol=1e-10)
+    loose = pd.DataFrame(g["scores_ref"], columns=result.columns)
+    for col in ("dc", "wr", "wcr"):
+        err = np.abs(result[col].values - ref[col].values)
+        bulk = ref[col].values >= ref[col].values.max() - 11.0          # where sklearn-exact is exact
+        assert err[bulk].max() <= 1e-4, (col, err[bulk].max())
+        assert np.abs(result[col].values - loose[col].values)[bulk].max() <= 5e-2
+    # accept decisions: identical to the reference's outside the tolerance band
+    for m in (20, 2):
+        mine = emulator.accept_concentric(result.reset_index(drop=True), m_factor=m, seed=6)
+        gold = g["accept_m%d" % m]
+        u = np.random.RandomState(6).uniform(0, 1, len(ref))
+        lr = oaccept.log_ratio([ref["wcr"], ref["dc"], ref["wr"]],
+                               [np.log(abs(ref["wcr_jac"][0])), np.log(abs(ref["dc_jac"][0])), np.log(abs(ref["wr_jac"][0]))],
+                               [1, -1, -1], np.log(m))
+        trust = np.ones(len(ref), dtype=bool)
+        for col in ("dc", "wr", "wcr"):
+            trust &= ref[col].values >= ref[col].values.max() - 11.0
+        band = np.abs(lr - np.log(u)) <= 3e-4
+        assert np.array_equal(mine[trust & ~band], gold[trust & ~band])
+        assert (mine != gold).mean() < 0.02
+
+
+def test_calc_scores_keeps_per_chunk_semantics():
+    from skysampler_b200 import emulator
+    g = load_golden("driver_naive")
+    wide_cr, wide_r, deep_c, deep_smc, columns = _containers(g)
+    infodicts, samples = emulator.make_naive_infodicts(wide_cr, wide_r, deep_c, deep_smc, columns, nsamples=600,
+                                                       nchunks=2, bandwidth=0.1, rmax=0.4)
+    sc = emulator.calc_scores(infodicts[0])
+    assert list(sc.columns) == ["dc", "dc_jac", "wr", "wr_jac", "wcr", "wcr_jac"] and len(sc) == 300
+    assert np.all(np.isfinite(sc.values))
+
+
+def test_classifier_layout_columns():
+    from skysampler_b200 import emulator, KDEContainer
+    g = load_golden("driver_naive")
+    wide_cr, wide_r, deep_c, deep_smc, columns = _containers(g)
+    rands = {"container": KDEContainer(pd.DataFrame(g["wide_cr"][::-1].copy(), columns=["C0", "C1", "C2", "LOGR"]),
+                                       pd.Series(g["w_cr"][::-1].copy()), seed=31)}
+    infodicts, samples = emulator.make_classifier_infodicts(wide_cr, wide_r, rands, deep_c, deep_smc, columns,
+                                                            nsamples=800, nchunks=3, bandwidth=0.1, rmax=0.4)
+    res = emulator.run_scores2(infodicts)
+    assert list(res.columns) == ["dc", "dc_jac", "wr", "wr_jac", "wcr_clust", "wcr_clust_jac", "wcr_rands", "wcr_rands_jac"]
+    assert len(res) == 800 and np.all(np.isfinite(res.values))
+    one = emulator.calc_scores2(infodicts[1])
+    assert list(one.columns) == list(res.columns)
+
+
+def test_fused_ratio_accept_equals_oracle_decisions():
+    """skb_ratio_accept: K KDEs of different dimension, column subsets of one table, accept in the epilogue."""
+    from skysampler_b200 import emulator, KDEContainer, synth
+    from oracle import brute64, draw
+    rs = np.random.RandomState(3)
+    n = 4000
+    tab = pd.DataFrame(np.column_stack([synth.mixture(3, n, 41), 0.3 * rs.normal(size=n)]), columns=["C0", "C1", "C2", "LOGR"])
+    conts, colsets = [], [["C0", "C1", "C2", "LOGR"], ["C0", "C1", "C2"], ["LOGR"]]
+    for k, cs in enumerate(colsets):
+        x = tab[cs].values + 0.1 * rs.normal(size=(n, len(cs)))
+        c = KDEContainer(pd.DataFrame(x, columns=cs), pd.Series(synth.wide_weights(n, 50 + k)), seed=60 + k)
+        c.standardize_data(); c.construct_kde(0.1)
+        conts.append(c)
+    m = 6000
+    prop = pd.DataFrame(tab.values[rs.randint(0, n, m)] + 0.15 * rs.normal(size=(m, 4)), columns=tab.columns)
+    u = rs.uniform(size=m)
+    out = emulator.score_group(conts, colsets, prop, sign=[1, -1, -1], log_m=np.log(20.0), u=u, band=2e-4)
+    refs = []
+    for c, cs in zip(conts, colsets):
+        z = np.asarray(c._data)
+        zq = np.asarray(c.pca_transform(prop[cs]))
+        refs.append(brute64.score(z, np.asarray(c.weights), 0.1, zq))
+    for lp, ref in zip(out["logp"], refs):
+        near = ref >= ref.max() - 100
+        assert np.abs(lp - ref)[near].max() <= 1e-4
+    lr = oaccept.log_ratio(refs, [np.log(abs(c._jacobian_det)) for c in conts], [1, -1, -1], np.log(20.0))
+    assert np.abs(out["log_ratio"] - lr).max() <= 3e-4
+    gold = np.log(u) < lr
+    band = np.abs(lr - np.log(u)) <= 4e-4
+    assert np.array_equal(out["accept"][~band], gold[~band])
+    assert out["in_band"].sum() <= band.sum() + 5 and 0 < gold.sum() < m
+    # and the probability-space form the reference uses gives the same decisions
+    ref_mask, _ = oaccept.accept(refs[1], conts[1]._jacobian_det, refs[2], conts[2]._jacobian_det,
+                                 refs[0], conts[0]._jacobian_det, m_factor=20, uniform=u)
+    assert np.array_equal(out["accept"][~band], np.asarray(ref_mask)[~band])
+    for c in conts:
+        c.drop_kde()

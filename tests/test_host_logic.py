@@ -1,0 +1,115 @@
+"""Host-side mirror of the reference surface (no GPU needed): whitening, partition, pickling, columns."""
+import pickle
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import load_golden
+from skysampler_b200 import KDEContainer, emulator, synth
+from oracle import draw
+
+
+def test_fit_pca_reproduces_reference_whitening(c1_train):
+    """Same seed, same rng consumption (emulator.py:286-320) -> same mean1 / components / std2 / jac."""
+    data, weights, cols = c1_train
+    for case, weighted in (("c1_score_w_h0p1", True), ("c1_score_u_h0p1", False)):
+        g = load_golden(case)
+        c = KDEContainer(pd.DataFrame(data, columns=cols), pd.Series(weights) if weighted else None, seed=11)
+        c.standardize_data()
+        np.testing.assert_allclose(np.asarray(c.mean1), g["mean1"], rtol=1e-13)
+        np.testing.assert_allclose(c.pca.components_, g["components"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(c.std2, g["std2"], rtol=1e-12)
+        assert abs(c._jacobian_det - float(g["jac"])) <= 1e-11 * abs(float(g["jac"]))
+        np.testing.assert_allclose(np.asarray(c._data)[:64], g["whitened_train_head"], rtol=0, atol=1e-11)
+        # the folded affine maps handed to the kernels are the same transform
+        mu, W, Winv = c.whitening_maps()
+        z = (data - mu) @ W
+        np.testing.assert_allclose(z, np.asarray(c._data), rtol=0, atol=1e-11)
+        np.testing.assert_allclose(z @ Winv + mu, data, rtol=0, atol=1e-11)
+        np.testing.assert_allclose(c.pca_inverse_transform(np.asarray(c._data)).values, data, rtol=0, atol=1e-11)
+        assert abs(abs(np.linalg.det(Winv)) - abs(c._jacobian_det)) < 1e-9 * abs(c._jacobian_det)
+
+
+def test_set_whitening_equals_oracle_transform(c1_train):
+    data, weights, cols = c1_train
+    g = load_golden("c1_score_w_h0p05")
+    c = KDEContainer(pd.DataFrame(data, columns=cols), pd.Series(weights))
+    c.set_whitening(g["mean1"], g["pca_mean"], g["components"], g["std2"])
+    np.testing.assert_allclose(np.asarray(c._data),
+                               draw.whiten(data, g["mean1"], g["pca_mean"], g["components"], g["std2"]),
+                               rtol=0, atol=1e-12)
+
+
+def test_constructor_defaults_and_surface():
+    df, w = synth.frame(3, 50, 1)
+    c = KDEContainer(df)                              # weights=None -> ones (emulator.py:252-253)
+    assert c.ndim == 3 and list(c.columns) == list(df.columns)
+    assert np.array_equal(c.weights, np.ones(50))
+    for name in ("set_seed", "shuffle", "sample", "fit_pca", "pca_transform", "pca_inverse_transform",
+                 "standardize_data", "select_subset", "construct_kde", "random_draw", "score_samples",
+                 "drop_kde", "drop_col"):
+        assert callable(getattr(c, name))
+    assert c._kernel == "gaussian" and c._breadth_first is False
+    c.drop_col("F0")
+    assert c.ndim == 2
+    c2 = KDEContainer(df, w, seed=3)
+    a = c2.rng.uniform()
+    c2.set_seed(3)
+    assert c2.rng.uniform() == a
+
+
+def test_row_sample_and_shuffle_keep_rows_aligned():
+    df, w = synth.frame(2, 200, 5)
+    c = KDEContainer(df.copy(), w.copy(), seed=1)
+    key = dict(zip(map(tuple, df.values), w.values))
+    c.shuffle()
+    assert len(c.data) == 200
+    assert all(key[tuple(r)] == ww for r, ww in zip(c.data.values, np.asarray(c.weights)))
+    c.sample(n=50)
+    assert len(c.data) == 50 and len(c.weights) == 50
+    c.sample(n=10 ** 6)                                # n > len -> falls back to frac (emulator.py:279-280)
+    assert len(c.data) == 50
+
+
+def test_container_pickles_after_drop_kde():
+    df, w = synth.frame(3, 300, 9)
+    c = KDEContainer(df, w, seed=2)
+    c.standardize_data()
+    c.drop_kde()
+    c2 = pickle.loads(pickle.dumps(c))
+    assert c2.pca is None and c2.kde is None
+    np.testing.assert_array_equal(c2._data, c._data)
+    assert c2.rng.uniform() == c.rng.uniform()
+
+
+def test_partition_follows_reference_rounding():
+    lst = np.arange(20)                                # utils.py:148-166 examples
+    assert [list(p) for p in emulator.partition(lst, 5)] == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9, 10, 11],
+                                                             [12, 13, 14, 15], [16, 17, 18, 19]]
+    assert [len(p) for p in emulator.partition(lst, 6)] == [3, 4, 3, 3, 4, 3]
+    parts = emulator.partition(list(range(1501)), 150)
+    assert sum(len(p) for p in parts) == 1501 and [x for p in parts for x in p] == list(range(1501))
+
+
+def test_accept_concentric_matches_golden_masks():
+    g = load_golden("driver_naive")
+    sc = pd.DataFrame(g["scores_exact"], columns=[str(c) for c in g["score_columns"]])
+    for m in (20, 2):
+        assert np.array_equal(emulator.accept_concentric(sc, m_factor=m, seed=6), g["accept_m%d" % m])
+
+
+def test_gaussian_kernel_only():
+    from skysampler_b200 import GaussianKDE
+    with pytest.raises(ValueError):
+        GaussianKDE(0.1, kernel="tophat")
+
+
+def test_synth_generators_are_seeded():
+    a = synth.mixture(4, 100, 7); b = synth.mixture(4, 100, 7)
+    assert np.array_equal(a, b) and a.shape == (100, 4)
+    w = synth.wide_weights(1000, 1)
+    assert w.min() >= 0.5 and w.max() <= 2.0 and len(np.unique(w)) <= 100
+    m1, pm, comps, std2 = synth.whiten_params(a)
+    z = (a - m1) @ comps.T / std2
+    np.testing.assert_allclose(z.std(axis=0), 1.0, rtol=1e-10)
