@@ -80,6 +80,7 @@ struct skb_kde {
     Scratch counters;          // [ceil(M/FB)] int, zero between calls
     Scratch q_stage, out_stage, aux_stage, flag_stage;
     Scratch small;             // 2 x u64 device counters
+    double log_wmax = 0.0;
 };
 
 namespace skb {
@@ -168,6 +169,7 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
         fj.out_m = dj.out_m;
         fj.out_s = dj.out_s;
         fj.log_norm = dj.h->hk.log_norm;
+        fj.log_wmax = dj.h->log_wmax;
         fj.nsplit = nsplit[j];
         fj.sign = (grouped && g.sign) ? g.sign[j] : 0;
         fj.sign_logjac = (grouped && g.sign && g.log_abs_jac) ? g.sign[j] * g.log_abs_jac[j] : 0.0;
@@ -355,6 +357,7 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
         }
     }
     hk.log_norm = skb_log_knorm(d, h) - std::log(hk.sum_w) + std::log(wmax);
+    k->log_wmax = std::log(wmax);
 
     // ---- device buffers ----
     const size_t tile_bytes = (size_t)hk.ntiles * stage_floats(d) * sizeof(float);

@@ -64,6 +64,7 @@ struct FinJob {
     double* out_m;           // partial-mode outputs (natural-log m, s) or NULL
     double* out_s;
     double log_norm;
+    double log_wmax;         // partial-mode outputs carry the true weights: m += log(w_max)
     double sign_logjac;      // sign * log|jac|
     int nsplit;
     int sign;

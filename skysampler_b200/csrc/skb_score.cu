@@ -172,7 +172,7 @@ __device__ __forceinline__ void finalize_query(const FinTable& fin, int first, i
         const FinJob& fj = fin.fj[f];
         double mstar, S;
         merge_partials(fj.partial, fj.nsplit, M, r, mstar, S);
-        if (fj.out_m) { fj.out_m[r] = -mstar * LN2; fj.out_s[r] = S; }
+        if (fj.out_m) { fj.out_m[r] = fj.log_wmax - mstar * LN2; fj.out_s[r] = S; }
         const double lp = fj.log_norm + log(S) - mstar * LN2;
         if (fj.out_logp) fj.out_logp[r] = lp;
         log_ratio += fj.sign * lp + fj.sign_logjac;
@@ -417,7 +417,7 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
         for (int q = 0; q < Q; q++) {
             const long long r = qbase + (long long)q * NT + tid;
             if (r < M) {
-                if (myfin.out_m) { myfin.out_m[r] = -(double)mref[q] * LN2; myfin.out_s[r] = S[q]; }
+                if (myfin.out_m) { myfin.out_m[r] = myfin.log_wmax - (double)mref[q] * LN2; myfin.out_s[r] = S[q]; }
                 if (myfin.out_logp) myfin.out_logp[r] = myfin.log_norm + log(S[q]) - (double)mref[q] * LN2;
             }
         }

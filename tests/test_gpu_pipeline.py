@@ -42,7 +42,9 @@ def test_rejection_sampler_driver_slice_matches_reference():
         err = np.abs(result[col].values - ref[col].values)
         bulk = ref[col].values >= ref[col].values.max() - 11.0          # where sklearn-exact is exact
         assert err[bulk].max() <= 1e-4, (col, err[bulk].max())
-        assert np.abs(result[col].values - loose[col].values)[bulk].max() <= 5e-2
+        # (the shipped atol=rtol=1e-6 run is looser than this backend — SURVEY.md finding 6: its own
+        #  error reaches ~0.1 nats in the bulk of this data — so only its median is compared)
+        assert np.median(np.abs(result[col].values - loose[col].values)[bulk]) <= 1e-3
     # accept decisions: identical to the reference's outside the tolerance band
     for m in (20, 2):
         mine = emulator.accept_concentric(result.reset_index(drop=True), m_factor=m, seed=6)
