@@ -1,0 +1,88 @@
+"""In-process batched driver for the rejection step — the next-row replacement of the
+reference's ``run_scores`` process pool + offline ``read_concentric`` accept (emulator.py:698-748).
+
+One ``RatioSampler.step`` = score a batch of proposal rows against every KDE of the group, form
+``log p_ref - log p_proposal - log m`` and the accept decision in the scoring kernel's epilogue
+(``skb_ratio_accept``), then pack the accepted rows in input order (``skb_compact``).  PyTorch
+supplies device buffers, pinned host buffers and the stream; the arithmetic is all in libskb.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import check, ptr, stream_ptr
+
+
+class RatioSampler(object):
+    def __init__(self, kdes, signs, log_abs_jac=None, log_m=0.0, band=2e-4, cols=None):
+        """kdes: fitted GaussianKDE objects on one device; signs[k] = +1 (reference density) / -1 (proposal).
+        cols[k]: column indices of the proposal table feeding KDE k (None -> first d columns)."""
+        self.kdes = list(kdes)
+        self.K = len(self.kdes)
+        self.device = torch.device("cuda", self.kdes[0].device_)
+        self.handles = (C.c_void_p * self.K)(*[k._handle() for k in self.kdes])
+        self.sign = np.ascontiguousarray(signs, dtype=np.int32)
+        self.log_abs_jac = np.ascontiguousarray(np.zeros(self.K) if log_abs_jac is None else log_abs_jac, dtype=np.float64)
+        self.log_m = float(log_m)
+        self.band = float(band)
+        self.cols = None
+        if cols is not None:
+            self.cols = np.full((self.K, _cabi.SKB_MAXD), -1, dtype=np.int32)
+            for k, cs in enumerate(cols):
+                self.cols[k, :len(cs)] = cs
+        self.pairs_per_row = int(sum(k.n_train_ for k in self.kdes))
+        self._buf = {}
+
+    def _get(self, name, shape, dtype):
+        t = self._buf.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self._buf[name] = t
+        return t
+
+    def score_accept(self, q, u, want_logp=False, want_ratio=False, stream=None):
+        """Device tensors in, device tensors out; asynchronous on ``stream`` (default: current)."""
+        M, ld = q.shape
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        accept = self._get("accept", (M,), torch.uint8)
+        in_band = self._get("in_band", (M,), torch.uint8)
+        logp = self._get("logp", (self.K, M), torch.float64) if want_logp else None
+        ratio = self._get("ratio", (M,), torch.float64) if want_ratio else None
+        check(_cabi.lib().skb_ratio_accept(self.handles, self.K, ptr(self.sign), ptr(self.log_abs_jac), self.log_m,
+                                           ptr(q), _cabi.dtype_code(q), M, ld, ptr(self.cols), ptr(u), self.band,
+                                           ptr(logp), ptr(ratio), ptr(accept), ptr(in_band), stream_ptr(st)))
+        return accept, in_band, logp, ratio
+
+    def compact(self, accept, rows, stream=None, sync_count=True):
+        """Accepted rows in input order (``samples[inds]``, emulator.py:746-747)."""
+        M, ld = rows.shape
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        out = self._get("packed", (M, ld), rows.dtype)
+        cnt = C.c_int64(0)
+        check(_cabi.lib().skb_compact(ptr(accept), M, ptr(rows), _cabi.dtype_code(rows), ld, ptr(out), None,
+                                      C.byref(cnt) if sync_count else None, stream_ptr(st)))
+        return out, int(cnt.value)
+
+    def step(self, q, u):
+        """Device-resident batch: returns (accepted rows [n_acc, ld] view, n_acc)."""
+        accept, _, _, _ = self.score_accept(q, u)
+        out, n = self.compact(accept, q)
+        return out[:n], n
+
+    def step_host(self, q_host, u_host, flags_host=None):
+        """End-to-end batch from (pinned) host memory: H2D of rows + uniforms, fused score/accept,
+        compaction, D2H of the accept flags and the accepted rows' count."""
+        M, ld = q_host.shape
+        qd = self._get("q_in", (M, ld), q_host.dtype)
+        ud = self._get("u_in", (M,), torch.float64)
+        qd.copy_(q_host, non_blocking=True)
+        ud.copy_(u_host, non_blocking=True)
+        accept, _, _, _ = self.score_accept(qd, ud)
+        out, n = self.compact(accept, qd)
+        if flags_host is None:
+            flags_host = torch.empty(M, dtype=torch.uint8, pin_memory=True)
+        flags_host.copy_(accept, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return flags_host, n, out[:n]

@@ -8,12 +8,17 @@ import numpy as np
 import pandas as pd
 
 
-def mixture(d, n, seed, k=8, cov_scale=1.0):
-    """G(d, n, seed): K=8 Gaussians, means ~ N(0, 2^2 I), cov = A A^T with A = I + 0.3 N(0,1)."""
+def mixture(d, n, seed, k=8, cov_scale=1.0, sample_seed=None):
+    """G(d, n, seed): K=8 Gaussians, means ~ N(0, 2^2 I), cov = A A^T with A = I + 0.3 N(0,1).
+
+    ``sample_seed`` draws a different sample from the SAME mixture (optionally with ``cov_scale``): the
+    cluster / field pair of the ratio workload must overlap, like a cluster line of sight and its field."""
     rng = np.random.RandomState(seed)
     means = rng.normal(0.0, 2.0, size=(k, d))
     mats = np.eye(d)[None, :, :] + 0.3 * rng.normal(size=(k, d, d))
     pis = rng.dirichlet(np.ones(k))
+    if sample_seed is not None:
+        rng = np.random.RandomState(sample_seed)
     comp = rng.choice(k, size=n, p=pis)
     z = rng.normal(size=(n, d))
     x = means[comp] + np.einsum("nij,nj->ni", mats[comp], z) * np.sqrt(cov_scale)
