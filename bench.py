@@ -262,8 +262,11 @@ def run_ours(args):
 
     # ---- proposal bound m: 99.9th percentile of the density ratio on a 1e5 pilot ----
     sampler = RatioSampler(kdes, signs=[1, -1], log_abs_jac=ljac, log_m=0.0)
-    npilot = min(100000, pool_rows)
-    _, _, _, ratio = sampler.score_accept(pool[:npilot], u_pool[:npilot], want_ratio=True)
+    # (pilot rows are taken from the un-inflated part of the first batch: in the inflated tail both
+    #  densities hang on single neighbours and the ratio is noise spanning hundreds of nats)
+    p0 = args.batch // 10
+    npilot = min(100000, args.batch - p0)
+    _, _, _, ratio = sampler.score_accept(pool[p0:p0 + npilot], u_pool[p0:p0 + npilot], want_ratio=True)
     log_m = float(torch.quantile(ratio[torch.isfinite(ratio)], 0.999).item())
     sampler.log_m = log_m
     torch.cuda.synchronize()
