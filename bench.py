@@ -234,6 +234,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("SKB_NCCL_DEBUG", "WARN")    # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = _cabi.lib()
 

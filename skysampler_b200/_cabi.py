@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libskb.so")
+LIB_PATH = os.environ.get("SKB_LIB_PATH") or os.path.join(_HERE, "csrc", "libskb.so")
 
 SKB_MAXD = 16
 SKB_MAX_GROUP = 8

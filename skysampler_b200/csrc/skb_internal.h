@@ -19,7 +19,25 @@ constexpr int NT = 128;              // threads per CTA of the score kernel
 constexpr int FB = 256;              // queries per finalize block (arrival-counter granularity)
 constexpr float PAD_COORD = 1.0e18f; // coordinate of padding / zero-weight points: exp2(-1e36) == 0
 
-__host__ __device__ constexpr int queries_per_thread(int D) { return D <= 4 ? 8 : (D <= 8 ? 4 : 2); }
+#ifndef SKB_Q_LE2
+#define SKB_Q_LE2 8
+#endif
+#ifndef SKB_Q_LE4
+#define SKB_Q_LE4 8
+#endif
+#ifndef SKB_Q_LE8
+#define SKB_Q_LE8 4
+#endif
+#ifndef SKB_Q_LE16
+#define SKB_Q_LE16 2
+#endif
+// resident CTAs per SM the register allocator is asked to allow (measured on B200, tools/perf_scan.py:
+// d<=3 and d>=9 like 4 CTAs/SM with 128 registers, d=4 likes 2 CTAs with 232, d=5..8 like 3 with 168)
+__host__ __device__ constexpr int min_blocks_per_sm(int D) { return D <= 3 ? 4 : (D == 4 ? 2 : (D <= 8 ? 3 : 4)); }
+__host__ __device__ constexpr int queries_per_thread(int D)
+{
+    return D <= 2 ? SKB_Q_LE2 : (D <= 4 ? SKB_Q_LE4 : (D <= 8 ? SKB_Q_LE8 : SKB_Q_LE16));
+}
 __host__ __device__ constexpr int stage_floats(int D) { return (D + 1) * TN; }
 
 // Device-resident description of one fitted KDE (one per handle, uploaded at skb_create).

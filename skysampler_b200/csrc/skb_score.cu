@@ -93,12 +93,25 @@ constexpr int SUB = 64;                           // points per overflow-checked
 //   MIN_ONLY = false:  sum2[q] += w_j * 2^(m_q - acc_j)      (packed halves = even / odd points)
 //   MIN_ONLY = true :  amin[q]  = min(amin[q], acc_j - m_q)  (no SFU work)
 // ---------------------------------------------------------------------------------------------
+#ifndef SKB_UNROLL
+#define SKB_UNROLL 1
+#endif
+#ifndef SKB_SWP
+#define SKB_SWP 0          // 1: software-pipeline the weighted accumulate one step behind the MUFUs
+#endif
+
 template <int D, int Q, bool MIN_ONLY>
 __device__ __forceinline__ void tile_pass(const float* __restrict__ tile, int npts,
                                           const u64 (&q2)[Q][D], const u64 (&nm2)[Q],
                                           u64 (&sum2)[Q], float (&amin)[Q])
 {
-#pragma unroll 1
+#if SKB_SWP
+    u64 epa[Q], epb[Q], wpa = 0, wpb = 0;      // previous step's terms and weights (weight 0 => no-op)
+#pragma unroll
+    for (int q = 0; q < Q; q++) { epa[q] = 0; epb[q] = 0; }
+#endif
+    constexpr int kUnroll = SKB_UNROLL;
+#pragma unroll kUnroll
     for (int j = 0; j < npts; j += 4) {
         u64 xa[D], xb[D];
 #pragma unroll
@@ -130,13 +143,32 @@ __device__ __forceinline__ void tile_pass(const float* __restrict__ tile, int np
                 amin[q] = min3(amin[q], a0, a1);
                 amin[q] = min3(amin[q], b0, b1);
             } else {
+#if SKB_SWP
+                sum2[q] = fma2(wpa, epa[q], sum2[q]);
+                sum2[q] = fma2(wpb, epb[q], sum2[q]);
+                epa[q] = pk(ex2_neg(a0), ex2_neg(a1));
+                epb[q] = pk(ex2_neg(b0), ex2_neg(b1));
+#else
                 const u64 ea = pk(ex2_neg(a0), ex2_neg(a1));
                 const u64 eb = pk(ex2_neg(b0), ex2_neg(b1));
                 sum2[q] = fma2(wa, ea, sum2[q]);
                 sum2[q] = fma2(wb, eb, sum2[q]);
+#endif
             }
         }
+#if SKB_SWP
+        wpa = wa; wpb = wb;
+#endif
     }
+#if SKB_SWP
+    if (!MIN_ONLY) {
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            sum2[q] = fma2(wpa, epa[q], sum2[q]);
+            sum2[q] = fma2(wpb, epb[q], sum2[q]);
+        }
+    }
+#endif
 }
 
 // log p (natural) of query r from the per-split partials of one job.
@@ -191,7 +223,7 @@ __device__ __forceinline__ void finalize_query(const FinTable& fin, int first, i
 // The score kernel.  grid = (query blocks, jobs, training splits), block = NT threads.
 // ---------------------------------------------------------------------------------------------
 template <int D>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, min_blocks_per_sm(D))
 skb_score_kernel(const __grid_constant__ ScoreLaunch L)
 {
     constexpr int Q = queries_per_thread(D);

@@ -214,7 +214,7 @@ def test_query_permutation_and_training_order_invariance():
     kde = _kde(z, None, 0.1)
     lp = kde.score_samples(q)
     perm = rs.permutation(len(q))
-    assert np.array_equal(kde.score_samples(q[perm]), lp[perm]) or np.abs(kde.score_samples(q[perm]) - lp[perm]).max() < 2e-5
+    assert np.array_equal(kde.score_samples(q[perm]), lp[perm])
     kde.close()
     # adversarial training order: sorted by distance from the origin, farthest first, so the running
     # reference exponent must be recentred again and again (overflow re-run path)
@@ -227,8 +227,25 @@ def test_query_permutation_and_training_order_invariance():
     _cabi.lib().skb_debug_counters(0, st, 1)
     assert st[0] > 0, "the sorted order was expected to exercise the re-run path"
     _check(lps, brute64.score(z, None, 0.1, q))
-    assert np.abs(lps - lp).max() <= 5e-5
+    near = lp >= lp.max() - 100.0
+    assert np.abs(lps - lp)[near].max() <= 5e-5
     ks.close()
+
+
+def test_results_do_not_depend_on_batching():
+    """The launch plan is a function of the fitted KDE only: any slice, chunk or shard of the query table
+    gives bit-identical log-densities (what makes k-GPU query sharding reproduce 1 GPU bit for bit)."""
+    rs = np.random.RandomState(21)
+    for n, d in ((300000, 8), (40000, 4), (3000, 2)):
+        z = rs.normal(size=(n, d)); w = rs.uniform(0.5, 2, n)
+        q = 1.5 * rs.normal(size=(9000, d))
+        kde = _kde(z, w, 0.1)
+        full = kde.score_samples(q)
+        for a, b in ((0, 1), (0, 4500), (4500, 9000), (123, 1147), (8999, 9000)):
+            assert np.array_equal(kde.score_samples(q[a:b]), full[a:b]), (n, d, a, b)
+        perm = rs.permutation(len(q))
+        assert np.array_equal(kde.score_samples(q[perm]), full[perm])
+        kde.close()
 
 
 def test_far_tail_queries_never_underflow():

@@ -1,0 +1,29 @@
+"""Throughput of the score kernel per feature dimension for the library named by SKB_LIB_PATH."""
+import sys, os, ctypes as C
+sys.path.insert(0, ".")
+import numpy as np, torch
+from skysampler_b200 import GaussianKDE, _cabi
+lib = _cabi.lib()
+fma, ex2 = C.c_double(), C.c_double()
+lib.skb_measure_pipes(0, 100.0, C.byref(fma), C.byref(ex2))
+dims = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [1, 2, 3, 4, 6, 8, 12, 16]
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 400000
+for d in dims:
+    m = (1 << 20) if d <= 8 else (1 << 19)
+    x = np.random.RandomState(1).normal(size=(n, d))
+    kde = GaussianKDE(0.1).fit(x)
+    q = torch.randn(m, d, dtype=torch.float64, device="cuda")
+    out = kde.score_samples(q)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(3):
+        kde.score_samples(q, out=out)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    rate = n * m / ms * 1e3
+    peak = min(fma.value / (2 * d + 1), ex2.value)
+    st = (C.c_uint64 * 4)(); lib.skb_debug_counters(0, st, 1)
+    print("%s d=%2d N=%d M=%d %8.2f ms  %.3e pairs/s  frac=%.3f  rerun=%.4f" % (
+        os.path.basename(_cabi.LIB_PATH), d, n, m, ms, rate, rate / peak, st[0] / max(st[1], 1)), flush=True)
+    kde.close()
