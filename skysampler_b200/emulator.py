@@ -232,3 +232,93 @@ def accept_concentric(scores, m_factor=20, seed=6, uniform=None):
     p_ref = wcr_score
     inds = uniform < p_ref / p_proposal
     return np.asarray(inds)
+
+
+# ------------------------------------------------------------------------------------------------
+# Bandwidth cross-validation (emulator.py:397-490) — the third caller of construct_kde/score_samples
+# ------------------------------------------------------------------------------------------------
+class KFoldCV(object):
+    """k-fold bandwidth CV on the B200 backend; same constructor / methods as emulator.py:397-458.
+
+    The reference fans each test fold out to ``nprocess`` pool workers but hands EVERY worker the first
+    partition (``iparts[0]`` at emulator.py:430-431), so its score is the weighted mean over the first
+    1/nprocess of the fold.  ``reference_bug_compat=True`` reproduces that; the default scores the whole
+    fold (the evident intent).  Either way one fold = one ``score_samples`` call here.
+    """
+
+    def __init__(self, cont, nfold=5, nprocess=100, seed=None, reference_bug_compat=False):
+        self.cont = cont
+        self.cont.standardize_data()
+        self.nfold = nfold
+        self.nprocess = nprocess
+        self.seed = seed
+        self.rng = np.random.RandomState(seed)
+        self.labels = self.rng.randint(0, self.nfold, len(self.cont.data))
+        self.reference_bug_compat = reference_bug_compat
+
+    def _loop_bandwidths(self, bandwidths):
+        scores = []
+        for bw in bandwidths:
+            scores.append(self._loop_cv(bw))
+        return scores
+
+    def _loop_cv(self, bandwidth):
+        mscores = []
+        for ifold in np.arange(self.nfold):
+            train, test = self._split(ifold)
+            iarr = np.arange(len(test.data))
+            iparts = partition(iarr, self.nprocess)
+            if self.reference_bug_compat:
+                sel = np.concatenate([iparts[0]] * len(iparts)) if len(iparts[0]) else iparts[0]
+            else:
+                sel = iarr
+            info = {
+                "train": train,
+                "test_data": test.data.iloc[sel],
+                "test_weights": pd.Series(np.asarray(test.weights))[sel] if not isinstance(test.weights, pd.Series)
+                else test.weights.iloc[sel],
+                "bandwidth": bandwidth,
+            }
+            result = run_cv_scores([info])
+            # (the reference takes log(jac) of a determinant whose sign is arbitrary, emulator.py:437; the
+            #  density needs |J| — as read_concentric uses it, :737-739)
+            mscore = np.sum(result["weights"] * (result["scores"] + np.log(np.abs(result["jac"])))) / np.sum(result["weights"])
+            mscores.append(mscore)
+        return mscores
+
+    def _split(self, label):
+        """splits data into train and test k-fold (emulator.py:442-450)"""
+        train = self._shrink(self.labels != label)
+        test = self._shrink(self.labels == label)
+        return train, test
+
+    def _shrink(self, index):
+        """emulator.py:452-458: shares the fitted whitening, re-whitens the subset."""
+        _cont = copy.copy(self.cont)
+        _cont.kde = None
+        _cont.data = _cont.data.iloc[index].copy()
+        if isinstance(_cont.weights, pd.Series):
+            _cont.weights = _cont.weights.iloc[index].copy()
+        else:
+            _cont.weights = np.asarray(_cont.weights)[index].copy()
+        _cont._data = _cont.pca_transform(_cont.data)
+        return _cont
+
+
+def _score_cv_samples(info):
+    """emulator.py:478-490."""
+    train = info["train"]
+    train.construct_kde(bandwidth=info["bandwidth"])
+    scores, jac = train.score_samples(info["test_data"])
+    train.kde.close()
+    train.kde = None
+    result = pd.DataFrame()
+    result["scores"] = scores
+    result["jac"] = np.ones(len(result)) * jac
+    result["weights"] = np.asarray(info["test_weights"])
+    return result
+
+
+def run_cv_scores(infodicts):
+    """emulator.py:461-475, in-process."""
+    return pd.concat([_score_cv_samples(info) for info in infodicts])

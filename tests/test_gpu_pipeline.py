@@ -124,3 +124,66 @@ def test_fused_ratio_accept_equals_oracle_decisions():
     assert np.array_equal(out["accept"][~band], np.asarray(ref_mask)[~band])
     for c in conts:
         c.drop_kde()
+
+
+def test_concentric_shells_batched_equals_per_shell_reference_flow():
+    """Config-3 shape scaled down: several shells, 4 KDEs each, one batched launch per dimension; the
+    scores must equal what calc_scores2 gives shell by shell and sit within 1e-4 of brute64."""
+    from skysampler_b200 import KDEContainer, concentric, synth
+    from oracle import brute64
+    rs = np.random.RandomState(7)
+    columns = {"cols_dc": ["C0", "C1", "C2"], "cols_wr": ["LOGR"], "cols_wcr": ["C0", "C1", "C2", "LOGR"]}
+    shells = []
+    for s in range(3):
+        n = 3000 + 500 * s
+        smc = synth.mixture(4, n, 700 + s)
+        wcr = synth.mixture(4, n, 710 + s); wcr[:, 3] = 0.3 * wcr[:, 3] - 0.2 + 0.1 * s
+        mk = lambda arr, cols, w, seed: {"container": KDEContainer(pd.DataFrame(arr, columns=cols), w, seed=seed)}
+        shells.append({
+            "deep_smc": mk(smc, ["MAG", "C0", "C1", "C2"], None, 1 + s),
+            "deep_c": mk(synth.mixture(4, n, 720 + s)[:, 1:], ["C0", "C1", "C2"], None, 11 + s),
+            "wide_cr_clust": mk(wcr, ["C0", "C1", "C2", "LOGR"], pd.Series(synth.wide_weights(n, 730 + s)), 21 + s),
+            "wide_cr_rands": mk(wcr[::-1].copy(), ["C0", "C1", "C2", "LOGR"], pd.Series(synth.wide_weights(n, 740 + s)), 31 + s),
+            "wide_r_ref": mk(0.3 * synth.mixture(1, n, 750 + s) - 0.2 + 0.1 * s, ["LOGR"], pd.Series(synth.wide_weights(n, 760 + s)), 41 + s),
+            "rmin": -0.5 + 0.1 * s, "rmax": 0.1 + 0.1 * s,
+        })
+    out = concentric.run_concentric(shells, columns, nsamples=2000, bandwidth=0.1, philox=True)
+    assert len(out) == 3
+    for sh, (samples, scores) in zip(shells, out):
+        assert list(scores.columns) == ["dc", "dc_jac", "wr", "wr_jac", "wcr_clust", "wcr_clust_jac", "wcr_rands", "wcr_rands_jac"]
+        assert len(samples) == 2000 and samples["LOGR"].between(sh["rmin"], sh["rmax"]).all()
+        assert np.all(np.isfinite(scores.values))
+        # oracle check of one KDE per shell with the whitening the run used (containers keep it)
+        c = sh["wide_cr_clust"]["container"]
+        mu, W, Winv = None, None, None
+        zq = (samples[columns["cols_wcr"]].values - (c.mean1 + c.pca_params["pca"].mean_)) @ (c.pca_params["pca"].components_.T / c.std2[None, :])
+        ref = brute64.score(np.asarray(c._data), np.asarray(c.weights), 0.1, zq)
+        near = ref >= ref.max() - 100
+        assert np.abs(scores["wcr_clust"].values - ref)[near].max() <= 1e-4
+
+
+def test_kfold_cv_bandwidth_scores():
+    """emulator.py:397-490 on the backend: CV score per bandwidth equals the oracle's weighted mean log-likelihood."""
+    from skysampler_b200 import KDEContainer, emulator, synth
+    from oracle import brute64
+    df, w = synth.frame(3, 4000, 77)
+    cont = KDEContainer(df, w, seed=5)
+    cv = emulator.KFoldCV(cont, nfold=3, nprocess=7, seed=9)
+    res = cv._loop_bandwidths([0.1, 0.3])
+    assert np.shape(res) == (2, 3)
+    z = np.asarray(cont._data); ww = np.asarray(cont.weights)
+    for ib, bw in enumerate((0.1, 0.3)):
+        for fold in range(3):
+            tr = cv.labels != fold; te = cv.labels == fold
+            lp = brute64.score(z[tr], ww[tr], bw, z[te])
+            ref = np.sum(ww[te] * (lp + np.log(abs(cont._jacobian_det)))) / np.sum(ww[te])
+            assert abs(res[ib][fold] - ref) <= 1e-4 * max(1.0, abs(ref))
+    # the reference's iparts[0] behaviour is reproducible on request
+    cvb = emulator.KFoldCV(KDEContainer(df, w, seed=5), nfold=3, nprocess=7, seed=9, reference_bug_compat=True)
+    rb = cvb._loop_cv(0.3)
+    te = np.nonzero(cvb.labels == 0)[0]
+    first = emulator.partition(np.arange(len(te)), 7)[0]
+    zz = np.asarray(cvb.cont._data); tr = cvb.labels != 0
+    lp = brute64.score(zz[tr], ww[tr], 0.3, zz[te][first])
+    ref = np.sum(ww[te][first] * (lp + np.log(abs(cvb.cont._jacobian_det)))) / np.sum(ww[te][first])
+    assert abs(rb[0] - ref) <= 1e-4 * max(1.0, abs(ref))
