@@ -33,7 +33,10 @@ constexpr float PAD_COORD = 1.0e18f; // coordinate of padding / zero-weight poin
 #endif
 // resident CTAs per SM the register allocator is asked to allow (measured on B200, tools/perf_scan.py:
 // d<=3 and d>=9 like 4 CTAs/SM with 128 registers, d=4 likes 2 CTAs with 232, d=5..8 like 3 with 168)
-__host__ __device__ constexpr int min_blocks_per_sm(int D) { return D <= 3 ? 4 : (D == 4 ? 2 : (D <= 8 ? 3 : 4)); }
+#ifndef SKB_MB_HI
+#define SKB_MB_HI 4
+#endif
+__host__ __device__ constexpr int min_blocks_per_sm(int D) { return D <= 3 ? 4 : (D == 4 ? 2 : (D <= 8 ? 3 : SKB_MB_HI)); }
 __host__ __device__ constexpr int queries_per_thread(int D)
 {
     return D <= 2 ? SKB_Q_LE2 : (D <= 4 ? SKB_Q_LE4 : (D <= 8 ? SKB_Q_LE8 : SKB_Q_LE16));

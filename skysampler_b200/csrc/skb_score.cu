@@ -93,80 +93,152 @@ constexpr int SUB = 64;                           // points per overflow-checked
 //   MIN_ONLY = false:  sum2[q] += w_j * 2^(m_q - acc_j)      (packed halves = even / odd points)
 //   MIN_ONLY = true :  amin[q]  = min(amin[q], acc_j - m_q)  (no SFU work)
 // ---------------------------------------------------------------------------------------------
-#ifndef SKB_UNROLL
-#define SKB_UNROLL 1
+#ifndef SKB_POLY_EXP
+#define SKB_POLY_EXP 1     // 1: for D == 1 a quarter of the exponentials run as a polynomial on the FMA pipe
 #endif
-#ifndef SKB_SWP
-#define SKB_SWP 0          // 1: software-pipeline the weighted accumulate one step behind the MUFUs
+#ifndef SKB_PREFETCH
+#define SKB_PREFETCH 0     // 1: double-buffer the tile words of the next 4 points in registers
 #endif
 
-template <int D, int Q, bool MIN_ONLY>
-__device__ __forceinline__ void tile_pass(const float* __restrict__ tile, int npts,
-                                          const u64 (&q2)[Q][D], const u64 (&nm2)[Q],
-                                          u64 (&sum2)[Q], float (&amin)[Q])
-{
-#if SKB_SWP
-    u64 epa[Q], epb[Q], wpa = 0, wpb = 0;      // previous step's terms and weights (weight 0 => no-op)
-#pragma unroll
-    for (int q = 0; q < Q; q++) { epa[q] = 0; epb[q] = 0; }
-#endif
-    constexpr int kUnroll = SKB_UNROLL;
-#pragma unroll kUnroll
-    for (int j = 0; j < npts; j += 4) {
-        u64 xa[D], xb[D];
+// the training-side operands of one step: 4 points as two packed pairs per dimension (+ weights)
+template <int D>
+struct StepOperands {
+    u64 xa[D], xb[D], wa, wb;
+    template <bool WITH_W>
+    __device__ __forceinline__ void load(const float* __restrict__ tile, int j)
+    {
 #pragma unroll
         for (int k = 0; k < D; k++) {
             const float4 v = *reinterpret_cast<const float4*>(tile + k * TN + j);
             xa[k] = pk(v.x, v.y);
             xb[k] = pk(v.z, v.w);
         }
-        u64 wa = 0, wb = 0;
-        if (!MIN_ONLY) {
+        if (WITH_W) {
             const float4 w4 = *reinterpret_cast<const float4*>(tile + D * TN + j);
             wa = pk(w4.x, w4.y);
             wb = pk(w4.z, w4.w);
+        } else {
+            wa = 0; wb = 0;
         }
-#pragma unroll
-        for (int q = 0; q < Q; q++) {
-            u64 aa = nm2[q], ab = nm2[q];
-#pragma unroll
-            for (int k = 0; k < D; k++) {
-                const u64 da = sub2(q2[q][k], xa[k]);
-                const u64 db = sub2(q2[q][k], xb[k]);
-                aa = fma2(da, da, aa);
-                ab = fma2(db, db, ab);
-            }
-            float a0, a1, b0, b1;
-            upk(aa, a0, a1);
-            upk(ab, b0, b1);
-            if (MIN_ONLY) {
-                amin[q] = min3(amin[q], a0, a1);
-                amin[q] = min3(amin[q], b0, b1);
-            } else {
-#if SKB_SWP
-                sum2[q] = fma2(wpa, epa[q], sum2[q]);
-                sum2[q] = fma2(wpb, epb[q], sum2[q]);
-                epa[q] = pk(ex2_neg(a0), ex2_neg(a1));
-                epb[q] = pk(ex2_neg(b0), ex2_neg(b1));
-#else
-                const u64 ea = pk(ex2_neg(a0), ex2_neg(a1));
-                const u64 eb = pk(ex2_neg(b0), ex2_neg(b1));
-                sum2[q] = fma2(wa, ea, sum2[q]);
-                sum2[q] = fma2(wb, eb, sum2[q]);
-#endif
-            }
-        }
-#if SKB_SWP
-        wpa = wa; wpb = wb;
-#endif
     }
-#if SKB_SWP
-    if (!MIN_ONLY) {
+};
+
+// {2^-a.lo, 2^-a.hi} on the FMA pipe: Cody-Waite split with the 1.5*2^23 magic constant and a degree-5
+// minimax polynomial of 2^f on [-0.5, 0.5] (max relative error 2.3e-7 in fp32 Horner form, the same
+// order as MUFU.EX2's), scaled by adding n << 23 to the exponent field.  8 packed FMA-pipe ops per two
+// terms (+ 2 IMAD, 4 FMNMX).  Used for a fixed quarter of the terms when D == 1, where the SFU is the
+// binding pipe and the FMA pipe is 3/8 busy: measured +4.5 % (4.45e12 -> 4.66e12 pairs/s on B200); at D == 2
+// the same offload LOSES 13 % (the FMA pipe becomes the limiter), so it is not applied there.  The argument is clamped to [-126, 125] so that
+// far points give <= 2^-125 (not garbage) and an exponent-window overflow still reads as >= 2^120.
+// Q independent polynomial exponentials, written stage-major so that the Q dependent chains interleave
+// (each stage is one packed FMA-pipe op per query; a single chain is 8 ops deep).
+template <int Q>
+__device__ __forceinline__ void exp2_neg_poly2_batch(u64 (&v)[Q])
+{
+    const u64 magic = pk(12582912.f, 12582912.f);
+    u64 t[Q], g[Q];
 #pragma unroll
-        for (int q = 0; q < Q; q++) {
-            sum2[q] = fma2(wpa, epa[q], sum2[q]);
-            sum2[q] = fma2(wpb, epb[q], sum2[q]);
+    for (int q = 0; q < Q; q++) {
+        float a0, a1;
+        upk(v[q], a0, a1);
+        a0 = fminf(fmaxf(a0, -126.f), 125.f);
+        a1 = fminf(fmaxf(a1, -126.f), 125.f);
+        v[q] = pk(a0, a1);
+    }
+#pragma unroll
+    for (int q = 0; q < Q; q++) t[q] = sub2(magic, v[q]);
+#pragma unroll
+    for (int q = 0; q < Q; q++) g[q] = sub2(t[q], magic);
+#pragma unroll
+    for (int q = 0; q < Q; q++) asm("add.rn.f32x2 %0, %1, %2;" : "=l"(g[q]) : "l"(v[q]), "l"(g[q]));
+#pragma unroll
+    for (int q = 0; q < Q; q++) v[q] = fma2(pk(-1.3276470126584172e-3f, -1.3276470126584172e-3f), g[q],
+                                            pk(9.675540961325169e-3f, 9.675540961325169e-3f));
+#pragma unroll
+    for (int q = 0; q < Q; q++) v[q] = fma2(v[q], g[q], pk(-5.550713464617729e-2f, -5.550713464617729e-2f));
+#pragma unroll
+    for (int q = 0; q < Q; q++) v[q] = fma2(v[q], g[q], pk(2.4022120237350464e-1f, 2.4022120237350464e-1f));
+#pragma unroll
+    for (int q = 0; q < Q; q++) v[q] = fma2(v[q], g[q], pk(-6.931469440460205e-1f, -6.931469440460205e-1f));
+#pragma unroll
+    for (int q = 0; q < Q; q++) v[q] = fma2(v[q], g[q], pk(1.0000001192092896f, 1.0000001192092896f));
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        float p0, p1, t0, t1;
+        upk(v[q], p0, p1);
+        upk(t[q], t0, t1);
+        v[q] = pk(__int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23)),
+                  __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23)));
+    }
+}
+
+template <int D, int Q, bool MIN_ONLY, bool POLY_B = false>
+__device__ __forceinline__ void step_compute(const StepOperands<D>& op, const u64 (&q2)[Q][D], const u64 (&nm2)[Q],
+                                             u64 (&sum2)[Q], float (&amin)[Q])
+{
+    u64 pb[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        u64 aa = nm2[q], ab = nm2[q];
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            const u64 da = sub2(q2[q][k], op.xa[k]);
+            const u64 db = sub2(q2[q][k], op.xb[k]);
+            aa = fma2(da, da, aa);
+            ab = fma2(db, db, ab);
         }
+        float a0, a1, b0, b1;
+        upk(aa, a0, a1);
+        upk(ab, b0, b1);
+        if (MIN_ONLY) {
+            amin[q] = min3(amin[q], a0, a1);
+            amin[q] = min3(amin[q], b0, b1);
+        } else {
+            const u64 ea = pk(ex2_neg(a0), ex2_neg(a1));
+            sum2[q] = fma2(op.wa, ea, sum2[q]);
+            if (POLY_B) {
+                pb[q] = ab;
+            } else {
+                const u64 eb = pk(ex2_neg(b0), ex2_neg(b1));
+                sum2[q] = fma2(op.wb, eb, sum2[q]);
+            }
+        }
+    }
+    if (POLY_B && !MIN_ONLY) {
+        exp2_neg_poly2_batch<Q>(pb);
+#pragma unroll
+        for (int q = 0; q < Q; q++) sum2[q] = fma2(op.wb, pb[q], sum2[q]);
+    }
+}
+
+// npts must be a multiple of 8.
+template <int D, int Q, bool MIN_ONLY>
+__device__ __forceinline__ void tile_pass(const float* __restrict__ tile, int npts,
+                                          const u64 (&q2)[Q][D], const u64 (&nm2)[Q],
+                                          u64 (&sum2)[Q], float (&amin)[Q])
+{
+#if SKB_PREFETCH
+    StepOperands<D> A, B;
+    A.template load<!MIN_ONLY>(tile, 0);
+#pragma unroll 1
+    for (int j = 0; j < npts; j += 8) {
+        B.template load<!MIN_ONLY>(tile, j + 4);
+        step_compute<D, Q, MIN_ONLY>(A, q2, nm2, sum2, amin);
+        const int jn = (j + 8 < npts) ? j + 8 : j;          // last iteration: harmless re-load
+        A.template load<!MIN_ONLY>(tile, jn);
+        step_compute<D, Q, MIN_ONLY>(B, q2, nm2, sum2, amin);
+    }
+#else
+    // which exponentials go to the FMA pipe depends on the point index only (points 8i+6, 8i+7 of a
+    // tile), never on the query slot, so a query's arithmetic stays independent of its batch position
+    constexpr bool kPoly = SKB_POLY_EXP && (D == 1) && !MIN_ONLY;
+#pragma unroll 1
+    for (int j = 0; j < npts; j += 8) {
+        StepOperands<D> A;
+        A.template load<!MIN_ONLY>(tile, j);
+        step_compute<D, Q, MIN_ONLY, false>(A, q2, nm2, sum2, amin);
+        A.template load<!MIN_ONLY>(tile, j + 4);
+        step_compute<D, Q, MIN_ONLY, kPoly>(A, q2, nm2, sum2, amin);
     }
 #endif
 }
