@@ -98,7 +98,6 @@ struct DeviceGuard {
 };
 
 // ---- launch planning --------------------------------------------------------------------------
-int score_ctas_per_sm(int D);   // skb_score.cu
 
 // Training-set splits of a launch.  The count depends on the fitted KDE ONLY (never on the number of
 // query rows), so the arithmetic a query sees — split boundaries, pilot tile, exponent-reference
@@ -196,7 +195,7 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
         if (done[j0]) continue;
         const int D = jobs[j0].h->hk.D;
         int nl = 0;
-        long long max_qblocks = 0;
+        long long max_rows = 0, total_rows_splits = 0;
         int max_split = 1;
         for (int j = j0; j < n; j++) {
             if (done[j] || jobs[j].h->hk.D != D) continue;
@@ -234,13 +233,16 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
                     sj.expected = nsplit[j];
                 }
             }
-            const int QB = NT * queries_per_thread(D);
-            const long long qb = (dj.M + QB - 1) / QB;
-            if (qb > max_qblocks) max_qblocks = qb;
+            if (dj.M > max_rows) max_rows = dj.M;
+            total_rows_splits += ((dj.M + NT * queries_per_thread(D) - 1) / (NT * queries_per_thread(D))) * nsplit[j];
             if (nsplit[j] > max_split) max_split = nsplit[j];
         }
+        // short query tables: fewer queries per thread -> more CTAs (same bits, see skb_internal.h)
+        const bool small_q = total_rows_splits < 2LL * jobs[j0].h->sms * score_ctas_per_sm(D, false);
+        const int QB = NT * (small_q ? queries_per_thread_small(D) : queries_per_thread(D));
+        const long long max_qblocks = (max_rows + QB - 1) / QB;
         if (max_qblocks > 0x7fffffffLL) return fail(SKB_EINVAL, "too many query rows for one launch");
-        if (max_qblocks > 0) SKB_CUDA(launch_score(D, L, nl, max_qblocks, max_split, st));
+        if (max_qblocks > 0) SKB_CUDA(launch_score(D, small_q, L, nl, max_qblocks, max_split, st));
     }
     return SKB_OK;
 }
@@ -443,8 +445,17 @@ static int score_one(skb_handle h, const void* q, int q_dtype, int64_t M, int64_
     for (double* o : outs) if (o && !is_device_ptr(o)) any_host_out = true;
     const GroupSpec g;
     if (q_dev && !any_host_out) {
-        DevJob dj{h, q, q_dtype == SKB_F32, q_is_whitened, M, ldq, cols, out_logp, out_m, out_s};
-        return run_jobs_device(&dj, 1, false, g, st);
+        // device resident: still walk the table in STAGE_ROWS chunks so the partial-state scratch stays bounded
+        const size_t esz_d = q_dtype == SKB_F32 ? 4 : 8;
+        for (int64_t a = 0; a < M; a += STAGE_ROWS) {
+            const int64_t m = (M - a < STAGE_ROWS) ? (M - a) : STAGE_ROWS;
+            DevJob dj{h, reinterpret_cast<const char*>(q) + (size_t)a * ldq * esz_d, q_dtype == SKB_F32, q_is_whitened,
+                      m, ldq, cols, out_logp ? out_logp + a : nullptr, out_m ? out_m + a : nullptr,
+                      out_s ? out_s + a : nullptr};
+            rc = run_jobs_device(&dj, 1, false, g, st);
+            if (rc) return rc;
+        }
+        return SKB_OK;
     }
     // staged path: chunks of rows through device scratch
     const size_t esz = q_dtype == SKB_F32 ? 4 : 8;
@@ -504,6 +515,7 @@ int skb_score_batch(const skb_job* jobs, int n_jobs, void* stream)
         for (int k = 0; k < j; k++)
             if (jobs[k].kde == jobs[j].kde) return fail(SKB_EINVAL, "a KDE handle may appear once per batch");
         if (jobs[j].M > 0 && (!is_device_ptr(jobs[j].q) || !is_device_ptr(jobs[j].out_logp))) all_dev = false;
+        if (jobs[j].M > STAGE_ROWS) all_dev = false;        // oversized tables take the chunked single-job path
     }
     if (!all_dev) {
         // host buffers: serial staged calls (still correct, just not one launch)
@@ -553,7 +565,7 @@ int skb_ratio_accept(const skb_handle* kdes, int n_kde, const int32_t* sign, con
     const bool ac_dev = !accept || is_device_ptr(accept);
     const bool ib_dev = !in_band || is_device_ptr(in_band);
     const bool all_dev = q_dev && u_dev && lp_dev && lr_dev && ac_dev && ib_dev;
-    const int64_t step = all_dev ? M : STAGE_ROWS;
+    const int64_t step = STAGE_ROWS;
     for (int64_t a = 0; a < M; a += step) {
         const int64_t m = (M - a < step) ? (M - a) : step;
         const void* qd = reinterpret_cast<const char*>(q) + (size_t)a * ldq * esz;

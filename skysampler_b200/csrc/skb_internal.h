@@ -16,7 +16,7 @@ typedef unsigned long long u64;
 constexpr int TN = 256;              // training points per tile
 constexpr int NSTAGE = 4;            // TMA ring depth
 constexpr int NT = 128;              // threads per CTA of the score kernel
-constexpr int FB = 256;              // queries per finalize block (arrival-counter granularity)
+constexpr int FB = 128;              // queries per finalize block (arrival-counter granularity)
 constexpr float PAD_COORD = 1.0e18f; // coordinate of padding / zero-weight points: exp2(-1e36) == 0
 
 #ifndef SKB_Q_LE2
@@ -41,6 +41,10 @@ __host__ __device__ constexpr int queries_per_thread(int D)
 {
     return D <= 2 ? SKB_Q_LE2 : (D <= 4 ? SKB_Q_LE4 : (D <= 8 ? SKB_Q_LE8 : SKB_Q_LE16));
 }
+// small-batch variant: fewer queries per thread -> more CTAs when the query table is short.  A query's
+// arithmetic does not depend on Q (each query is a private register chain), so both variants give
+// bit-identical results and the planner may pick either.
+__host__ __device__ constexpr int queries_per_thread_small(int D) { return D <= 8 ? 2 : 1; }
 __host__ __device__ constexpr int stage_floats(int D) { return (D + 1) * TN; }
 
 // Device-resident description of one fitted KDE (one per handle, uploaded at skb_create).
@@ -112,8 +116,9 @@ struct ScoreLaunch {
 cudaError_t launch_pack(const void* train, int f32, long long N, int D, long long ld, int is_whitened,
                         const KdeDev* kde_dev, const double* w, double inv_wmax,
                         float* tiles, double* zt64, int ntiles, cudaStream_t st);
-cudaError_t launch_score(int D, const ScoreLaunch& L, int njobs, long long max_qblocks, int max_split,
+cudaError_t launch_score(int D, bool small_q, const ScoreLaunch& L, int njobs, long long max_qblocks, int max_split,
                          cudaStream_t st);
+int score_ctas_per_sm(int D, bool small_q);
 cudaError_t launch_draw(const KdeDev* kde, int D, long long M, const double* u, const double* z,
                         uint64_t seed, uint64_t offset, const long long* rows,
                         int rcol, double rmin, double rmax, int max_attempts,

@@ -232,13 +232,22 @@ __device__ __forceinline__ void tile_pass(const float* __restrict__ tile, int np
     // which exponentials go to the FMA pipe depends on the point index only (points 8i+6, 8i+7 of a
     // tile), never on the query slot, so a query's arithmetic stays independent of its batch position
     constexpr bool kPoly = SKB_POLY_EXP && (D == 1) && !MIN_ONLY;
+    if (kPoly) {
 #pragma unroll 1
-    for (int j = 0; j < npts; j += 8) {
-        StepOperands<D> A;
-        A.template load<!MIN_ONLY>(tile, j);
-        step_compute<D, Q, MIN_ONLY, false>(A, q2, nm2, sum2, amin);
-        A.template load<!MIN_ONLY>(tile, j + 4);
-        step_compute<D, Q, MIN_ONLY, kPoly>(A, q2, nm2, sum2, amin);
+        for (int j = 0; j < npts; j += 8) {
+            StepOperands<D> A;
+            A.template load<!MIN_ONLY>(tile, j);
+            step_compute<D, Q, MIN_ONLY, false>(A, q2, nm2, sum2, amin);
+            A.template load<!MIN_ONLY>(tile, j + 4);
+            step_compute<D, Q, MIN_ONLY, kPoly>(A, q2, nm2, sum2, amin);
+        }
+    } else {
+#pragma unroll 1
+        for (int j = 0; j < npts; j += 4) {
+            StepOperands<D> A;
+            A.template load<!MIN_ONLY>(tile, j);
+            step_compute<D, Q, MIN_ONLY, false>(A, q2, nm2, sum2, amin);
+        }
     }
 #endif
 }
@@ -294,11 +303,10 @@ __device__ __forceinline__ void finalize_query(const FinTable& fin, int first, i
 // ---------------------------------------------------------------------------------------------
 // The score kernel.  grid = (query blocks, jobs, training splits), block = NT threads.
 // ---------------------------------------------------------------------------------------------
-template <int D>
-__global__ void __launch_bounds__(NT, min_blocks_per_sm(D))
+template <int D, int Q>
+__global__ void __launch_bounds__(NT, (Q == queries_per_thread(D) ? min_blocks_per_sm(D) : 4))
 skb_score_kernel(const __grid_constant__ ScoreLaunch L)
 {
-    constexpr int Q = queries_per_thread(D);
     constexpr int QB = NT * Q;
     constexpr int STAGE_FLOATS = stage_floats(D);
     constexpr uint32_t STAGE_BYTES = STAGE_FLOATS * sizeof(float);
@@ -613,15 +621,15 @@ cudaError_t launch_pack(const void* train, int f32, long long N, int D, long lon
     return cudaGetLastError();
 }
 
-template <int D>
-static cudaError_t launch_score_d(const ScoreLaunch& L, int njobs, long long max_qblocks, int max_split,
-                                  cudaStream_t st)
+template <int D, int Q>
+static cudaError_t launch_score_dq(const ScoreLaunch& L, int njobs, long long max_qblocks, int max_split,
+                                   cudaStream_t st)
 {
     const size_t smem = (size_t)NSTAGE * stage_floats(D) * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t);
-    cudaError_t e = cudaFuncSetAttribute(skb_score_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(skb_score_kernel<D, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)max_qblocks, (unsigned)njobs, (unsigned)max_split);
-    skb_score_kernel<D><<<grid, NT, smem, st>>>(L);
+    skb_score_kernel<D, Q><<<grid, NT, smem, st>>>(L);
     count_launch();
     return cudaGetLastError();
 }
@@ -636,41 +644,44 @@ cudaError_t read_stats(unsigned long long* out4, int reset)
     return e;
 }
 
-template <int D>
-static int occupancy_d()
+template <int D, int Q>
+static int occupancy_dq()
 {
     const size_t smem = (size_t)NSTAGE * stage_floats(D) * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t);
     int n = 0;
-    if (cudaFuncSetAttribute(skb_score_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, skb_score_kernel<D>, NT, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(skb_score_kernel<D, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, skb_score_kernel<D, Q>, NT, smem) != cudaSuccess) {
         cudaGetLastError();
         return 2;
     }
     return n > 0 ? n : 1;
 }
 
-int score_ctas_per_sm(int D)
+int score_ctas_per_sm(int D, bool small_q)
 {
-    static int cache[SKB_MAXD + 1] = {0};
+    static int cache[2][SKB_MAXD + 1] = {{0}, {0}};
     if (D < 1 || D > SKB_MAXD) return 1;
-    if (cache[D] == 0) {
+    int& c = cache[small_q ? 1 : 0][D];
+    if (c == 0) {
         switch (D) {
-#define SKB_CASE(d) case d: cache[D] = occupancy_d<d>(); break;
+#define SKB_CASE(d) case d: c = small_q ? occupancy_dq<d, queries_per_thread_small(d)>() \
+                                        : occupancy_dq<d, queries_per_thread(d)>(); break;
             SKB_CASE(1) SKB_CASE(2) SKB_CASE(3) SKB_CASE(4) SKB_CASE(5) SKB_CASE(6) SKB_CASE(7) SKB_CASE(8)
             SKB_CASE(9) SKB_CASE(10) SKB_CASE(11) SKB_CASE(12) SKB_CASE(13) SKB_CASE(14) SKB_CASE(15) SKB_CASE(16)
 #undef SKB_CASE
         }
     }
-    return cache[D];
+    return c;
 }
 
 static_assert(sizeof(ScoreLaunch) <= 4000, "ScoreLaunch must fit the classic 4 KB kernel-parameter space");
 
-cudaError_t launch_score(int D, const ScoreLaunch& L, int njobs, long long max_qblocks, int max_split,
+cudaError_t launch_score(int D, bool small_q, const ScoreLaunch& L, int njobs, long long max_qblocks, int max_split,
                          cudaStream_t st)
 {
     switch (D) {
-#define SKB_CASE(d) case d: return launch_score_d<d>(L, njobs, max_qblocks, max_split, st);
+#define SKB_CASE(d) case d: return small_q ? launch_score_dq<d, queries_per_thread_small(d)>(L, njobs, max_qblocks, max_split, st) \
+                                           : launch_score_dq<d, queries_per_thread(d)>(L, njobs, max_qblocks, max_split, st);
         SKB_CASE(1) SKB_CASE(2) SKB_CASE(3) SKB_CASE(4) SKB_CASE(5) SKB_CASE(6) SKB_CASE(7) SKB_CASE(8)
         SKB_CASE(9) SKB_CASE(10) SKB_CASE(11) SKB_CASE(12) SKB_CASE(13) SKB_CASE(14) SKB_CASE(15) SKB_CASE(16)
 #undef SKB_CASE
