@@ -365,14 +365,20 @@ def run_ours(args):
                     traffic = tj.get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
+        flop_pair = 3 * D + 1
         roof = {
-            "bound": "fp32_fma_pipe", "kernel": "skb::skb_score_kernel<8>",
-            "achieved": ach / 1e9, "peak": peak_pairs / 1e9, "unit": "Gpairs/s", "frac": ach / peak_pairs,
-            "traffic": traffic,
-            "peak_source": "measured live: FFMA2 %.3e lane-FMA/s / (2d+1=%d), MUFU.EX2 %.3e /s (skb_measure_pipes); "
-                           "MEASURED_PEAKS.json has no FP32/SFU figure" % (fma.value, 2 * D + 1, ex2.value),
-            "algorithmic_work_per_pair": "%d FP32-pipe lane ops (d FSUB + d FFMA + 1 FFMA) + 1 MUFU.EX2" % (2 * D + 1),
-            "achieved_fp32_tflops": ach * (3 * D + 1) / 1e12,
+            # bound: the FP32 FMA pipe (with the SFU as second limit) — not HBM, not tensor cores
+            "bound": "fp32", "kernel": "skb::skb_score_kernel<8,4>",
+            "achieved": ach * flop_pair / 1e12, "peak": peak_pairs * flop_pair / 1e12, "unit": "TFLOP/s",
+            "frac": ach / peak_pairs, "traffic": traffic,
+            "definition": "achieved = pairs/launch x (3d+1) algorithmic FP32 FLOP / CUDA-event launch time; "
+                          "peak = min(FFMA lane-ops/s / (2d+1), EX2/s) x (3d+1): the pair roofline of SURVEY.md "
+                          "§8d expressed in FLOP/s (a pair costs 2d+1 FMA-pipe lane ops, 3d+1 FLOP, 1 EX2)",
+            "achieved_gpairs": ach / 1e9, "peak_gpairs": peak_pairs / 1e9,
+            "fp32_fma_peak_tflops_measured": 2.0 * fma.value / 1e12, "ex2_peak_per_s_measured": ex2.value,
+            "frac_of_raw_fp32_flops": ach * flop_pair / (2.0 * fma.value),
+            "peak_source": "measured live on this GPU by skb_measure_pipes (FFMA2 and MUFU.EX2 saturation loops, "
+                           "300 ms each); MEASURED_PEAKS.json holds only HBM and bf16-tensor figures",
             "kernel_ms_per_launch": kernel_ms, "pairs_per_launch": pairs_per_step_rank,
             "hbm_gbs_peak_for_reference": _hbm_peak(),
             "rerun_blocks_frac": (st[0] / float(st[1])) if st[1] else None,
@@ -383,7 +389,8 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 pair terms, f64 log-sum-exp", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "dtype_note": "fp32 pair terms, fp64 log-sum-exp state",
+            "data": "synthetic",
             "config": workload_config(args, world),
             "accepted_samples_per_s": accepted / (ms_total * 1e-3),
             "accept_fraction": accepted / float(args.batch * world * args.steps), "log_m": log_m,
