@@ -3,6 +3,7 @@
 // error code.
 #include "skb_internal.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -75,11 +76,13 @@ struct skb_kde {
     KdeDev hk;                 // host copy of the device descriptor
     KdeDev* dk = nullptr;      // device descriptor
     float* tiles = nullptr;
+    float* boxes = nullptr;
+    int* perm = nullptr;       // fit-time only
     double* zt64 = nullptr;
     double* cumsum = nullptr;
     Scratch partial;           // [nsplit][M] double2
     Scratch counters;          // [ceil(M/FB)] int, zero between calls
-    Scratch q_stage, out_stage, aux_stage, flag_stage;
+    Scratch q_stage, out_stage, aux_stage, flag_stage, sort_stage;
     Scratch small;             // 2 x u64 device counters
     double log_wmax = 0.0;
 };
@@ -97,6 +100,28 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// ---- kd-tree ordering (host, fit time) ----------------------------------------------------------
+// Recursive median split along the widest coordinate; the left part always takes a whole number of
+// tiles so that every tile except the last is a full leaf of TN points.
+static void kd_order(const float* z, int D, int* idx, long long n)
+{
+    if (n <= TN) return;
+    float lo[SKB_MAXD], hi[SKB_MAXD];
+    for (int k = 0; k < D; k++) { lo[k] = INFINITY; hi[k] = -INFINITY; }
+    for (long long i = 0; i < n; i++) {
+        const float* p = z + (size_t)idx[i] * D;
+        for (int k = 0; k < D; k++) { if (p[k] < lo[k]) lo[k] = p[k]; if (p[k] > hi[k]) hi[k] = p[k]; }
+    }
+    int kbest = 0;
+    for (int k = 1; k < D; k++) if (hi[k] - lo[k] > hi[kbest] - lo[kbest]) kbest = k;
+    const long long ntile = (n + TN - 1) / TN;
+    const long long nl = ((ntile + 1) / 2) * TN;          // 0 < nl < n because n > TN
+    std::nth_element(idx, idx + nl, idx + n,
+                     [z, D, kbest](int a, int b) { return z[(size_t)a * D + kbest] < z[(size_t)b * D + kbest]; });
+    kd_order(z, D, idx, nl);
+    kd_order(z, D, idx + nl, n - nl);
+}
+
 // ---- launch planning --------------------------------------------------------------------------
 
 // Training-set splits of a launch.  The count depends on the fitted KDE ONLY (never on the number of
@@ -104,12 +129,21 @@ struct DeviceGuard {
 // history — is the same whatever batch, chunk or GPU it lands in: results are bit-identical under any
 // query sharding.  >= 128 tiles per split keeps the per-split pilot pass under 1 % (measured: 8 splits
 // cost 0.8 % against 1 on the bench workload, 32 cost 7 %).
+static bool cull_enabled()
+{
+    const char* e = getenv("SKB_NO_CULL");       // SKB_NO_CULL=1: evaluate every pair (roofline measurements)
+    return !(e && atoi(e) != 0);
+}
+
 static int plan_nsplit(const skb_kde* h, long long /*M*/, int /*njobs*/)
 {
     if (const char* f = getenv("SKB_FORCE_NSPLIT")) {
         int v = atoi(f);
         if (v >= 1) return v > h->hk.ntiles ? h->hk.ntiles : v;
     }
+    // with tile culling every CTA walks the box table of ALL tiles once; splitting the tiles over CTAs
+    // would repeat that walk per split, so the culled path never splits
+    if (cull_enabled()) return 1;
     int ns = h->hk.ntiles / 128;
     if (ns < 1) ns = 1;
     if (ns > 8) ns = 8;
@@ -183,6 +217,39 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
     L.fin.accept = g.accept;
     L.fin.in_band = g.in_band;
 
+    // ---- visit order of the query rows: Morton order in the prescaled space of the widest KDE ----
+    const bool cull = cull_enabled();
+    const int* perm_of[SKB_MAX_JOBS];
+    for (int j = 0; j < n; j++) perm_of[j] = nullptr;
+    if (cull) {
+        int lead = 0;
+        for (int j = 1; j < n; j++) if (jobs[j].h->hk.D > jobs[lead].h->hk.D) lead = j;
+        for (int j = 0; j < n; j++) {
+            if (grouped && j != lead) continue;
+            const DevJob& dj = jobs[j];
+            if (dj.M < 1024 || dj.M > 0x7fffffffLL) continue;
+            const size_t M_ = (size_t)dj.M;
+            const size_t tb = sort_temp_bytes(dj.M);
+            const size_t need = M_ * (8 + 8 + 4 + 4) + 64 + tb + 256;
+            SKB_CUDA(dj.h->sort_stage.reserve(need));
+            char* base = reinterpret_cast<char*>(dj.h->sort_stage.p);
+            unsigned long long* keys_in = reinterpret_cast<unsigned long long*>(base);
+            unsigned long long* keys_out = keys_in + M_;
+            int* idx_in = reinterpret_cast<int*>(keys_out + M_);
+            int* idx_out = idx_in + M_;
+            signed char* cols_dev = reinterpret_cast<signed char*>(idx_out + M_);
+            void* temp = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(cols_dev) + 64 + 255) & ~(uintptr_t)255);
+            signed char ch[SKB_MAXD];
+            for (int k = 0; k < SKB_MAXD; k++) ch[k] = (signed char)(k < dj.h->hk.D ? (dj.cols ? dj.cols[k] : k) : 0);
+            SKB_CUDA(cudaMemcpyAsync(cols_dev, ch, SKB_MAXD, cudaMemcpyHostToDevice, st));
+            SKB_CUDA(launch_query_order(dj.h->dk, dj.q, dj.q_f32, dj.M, dj.ldq, dj.q_is_whitened, cols_dev, keys_in,
+                                        keys_out, idx_in, idx_out, temp, tb, st));
+            perm_of[j] = idx_out;
+        }
+        if (grouped) for (int j = 0; j < n; j++) perm_of[j] = perm_of[lead];
+    }
+    for (int j = 0; j < n; j++) L.fin.fj[j].perm = perm_of[j];
+
     int* group_counters = nullptr;
     if (grouped) {
         const size_t nfb = (size_t)((jobs[0].M + FB - 1) / FB);
@@ -211,6 +278,8 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
             sj.q_is_whitened = dj.q_is_whitened;
             sj.nsplit = nsplit[j];
             sj.fin_slot = j;
+            sj.cull = cull ? 1 : 0;
+            sj.perm = perm_of[j];
             bool ident = true;
             for (int k = 0; k < D; k++) {
                 const int c = dj.cols ? dj.cols[k] : k;
@@ -364,8 +433,6 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
     k->log_wmax = std::log(wmax);
 
     // ---- device buffers ----
-    const size_t tile_bytes = (size_t)hk.ntiles * stage_floats(d) * sizeof(float);
-    SKB_CUDA_C(cudaMalloc(&k->tiles, tile_bytes));
     SKB_CUDA_C(cudaMalloc(&k->zt64, (size_t)N * d * sizeof(double)));
     if (w) {
         SKB_CUDA_C(cudaMalloc(&k->cumsum, (size_t)N * sizeof(double)));
@@ -374,7 +441,6 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
         SKB_CUDA_C(cudaMemcpy(d_w, wh.data(), (size_t)N * 8, cudaMemcpyHostToDevice));
     }
     SKB_CUDA_C(cudaMalloc(&k->dk, sizeof(KdeDev)));
-    hk.tiles = k->tiles;
     hk.zt64 = k->zt64;
     hk.cumsum_w = k->cumsum;
     SKB_CUDA_C(cudaMemcpy(k->dk, &hk, sizeof(KdeDev), cudaMemcpyHostToDevice));
@@ -387,9 +453,43 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
         SKB_CUDA_C(cudaMemcpy(d_train_tmp, train, bytes, cudaMemcpyHostToDevice));
         d_train = d_train_tmp;
     }
-    SKB_CUDA_C(launch_pack(d_train, train_dtype == SKB_F32, N, d, ld_train, train_is_whitened, k->dk, d_w,
-                           1.0 / wmax, k->tiles, k->zt64, hk.ntiles, 0));
+    // whitened fp64 rows (original order: the draw centres)
+    SKB_CUDA_C(launch_fit(d_train, train_dtype == SKB_F32, N, d, ld_train, train_is_whitened, k->dk, k->zt64, 0));
+
+    // ---- kd-tree order of the weighted points: every tile of TN points is one leaf ----
+    {
+        std::vector<double> zh((size_t)N * d);
+        SKB_CUDA_C(cudaMemcpy(zh.data(), k->zt64, zh.size() * 8, cudaMemcpyDeviceToHost));
+        std::vector<float> zf((size_t)N * d);
+        for (size_t i = 0; i < zf.size(); i++) zf[i] = (float)(zh[i] * hk.c);
+        std::vector<double>().swap(zh);
+        std::vector<int> order;
+        order.reserve((size_t)N);
+        for (int64_t i = 0; i < N; i++)
+            if (!w || wh[(size_t)i] > 0.0) order.push_back((int)i);
+        kd_order(zf.data(), d, order.data(), (long long)order.size());
+        hk.ntiles = (int)((order.size() + TN - 1) / TN);
+        for (int kk = 0; kk < d; kk++) { hk.glo[kk] = INFINITY; hk.ghi[kk] = -INFINITY; }
+        for (int idx : order)
+            for (int kk = 0; kk < d; kk++) {
+                const float v = zf[(size_t)idx * d + kk];
+                if (v < hk.glo[kk]) hk.glo[kk] = v;
+                if (v > hk.ghi[kk]) hk.ghi[kk] = v;
+            }
+        order.resize((size_t)hk.ntiles * TN, -1);
+        SKB_CUDA_C(cudaMalloc(&k->perm, order.size() * sizeof(int)));
+        SKB_CUDA_C(cudaMemcpy(k->perm, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    const size_t tile_bytes = (size_t)hk.ntiles * stage_floats(d) * sizeof(float);
+    SKB_CUDA_C(cudaMalloc(&k->tiles, tile_bytes));
+    SKB_CUDA_C(cudaMalloc(&k->boxes, (size_t)hk.ntiles * 2 * d * sizeof(float)));
+    SKB_CUDA_C(launch_pack(k->zt64, k->perm, d, hk.c, d_w, 1.0 / wmax, k->tiles, hk.ntiles, k->boxes, 0));
+    hk.tiles = k->tiles;
+    hk.boxes = k->boxes;
+    SKB_CUDA_C(cudaMemcpy(k->dk, &hk, sizeof(KdeDev), cudaMemcpyHostToDevice));
     SKB_CUDA_C(cudaStreamSynchronize(0));
+    cudaFree(k->perm);
+    k->perm = nullptr;
     SKB_CUDA_C(k->small.reserve(64, true));
 #undef SKB_CUDA_C
     rc = cleanup(SKB_OK);
@@ -403,11 +503,13 @@ int skb_destroy(skb_handle h)
     DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
     if (h->tiles) cudaFree(h->tiles);
+    if (h->boxes) cudaFree(h->boxes);
+    if (h->perm) cudaFree(h->perm);
     if (h->zt64) cudaFree(h->zt64);
     if (h->cumsum) cudaFree(h->cumsum);
     if (h->dk) cudaFree(h->dk);
     h->partial.release(); h->counters.release(); h->q_stage.release(); h->out_stage.release();
-    h->aux_stage.release(); h->flag_stage.release(); h->small.release();
+    h->aux_stage.release(); h->flag_stage.release(); h->sort_stage.release(); h->small.release();
     cudaGetLastError();
     delete h;
     return SKB_OK;

@@ -10,9 +10,12 @@ typedef unsigned long long u64;
 
 // ---- training-tile geometry -------------------------------------------------------------------
 // The fitted KDE lives in HBM as tiles of TN points in SoA order: tile t is one contiguous block
-//   [D+1][TN] fp32 = D rows of prescaled whitened coordinates + 1 row of normalised weights,
+//   [D+2][TN] fp32 = D rows of prescaled whitened coordinates + 1 row of normalised weights + 1 header
+//   row whose first 2D words are the tile's bounding box (lo[D], hi[D]),
 // so that ONE 1-D TMA bulk copy (cp.async.bulk, SASS UBLKCP) moves a whole tile into shared memory
 // and an LDS.128 of row k yields two packed {x_j, x_j+1} operands for FADD2/FFMA2.
+// Tiles are the leaves of a kd-tree over the training points (built on the host at fit time), so a
+// tile is spatially compact and its box test can prove that every pair term flushes to zero.
 constexpr int TN = 256;              // training points per tile
 constexpr int NSTAGE = 4;            // TMA ring depth
 constexpr int NT = 128;              // threads per CTA of the score kernel
@@ -45,13 +48,14 @@ __host__ __device__ constexpr int queries_per_thread(int D)
 // arithmetic does not depend on Q (each query is a private register chain), so both variants give
 // bit-identical results and the planner may pick either.
 __host__ __device__ constexpr int queries_per_thread_small(int D) { return D <= 8 ? 2 : 1; }
-__host__ __device__ constexpr int stage_floats(int D) { return (D + 1) * TN; }
+__host__ __device__ constexpr int stage_floats(int D) { return (D + 2) * TN; }   // D coords, weights, header (box)
 
 // Device-resident description of one fitted KDE (one per handle, uploaded at skb_create).
 struct KdeDev {
     const float* tiles;      // [ntiles][D+1][TN]
     const double* zt64;      // [N][D] whitened fp64 rows (draw centres)
     const double* cumsum_w;  // [N] sequential fp64 cumsum (NULL for unweighted)
+    const float* boxes;      // [ntiles][2][D] lo / hi of the packed fp32 coordinates
     long long N;
     int ntiles;
     int D;
@@ -61,6 +65,7 @@ struct KdeDev {
     double h;
     double sum_w;
     double log_norm;         // log_knorm - log(sum_w) + log(w_max)   (natural log)
+    float glo[SKB_MAXD], ghi[SKB_MAXD];   // bounding box of all packed points (Morton quantisation of queries)
     double mu[SKB_MAXD];
     double Wc[SKB_MAXD * SKB_MAXD];    // forward map prescaled by c:  c*z_k = sum_i (x_i-mu_i) Wc[i*D+k]
     double Winv[SKB_MAXD * SKB_MAXD];  // inverse map: x_i = sum_k z_k Winv[k*D+i] + mu_i
@@ -80,6 +85,8 @@ struct ScoreJob {
     int* counters;           // [ceil(M/FB)] arrival counters of the group (NULL -> finalize from registers)
     int expected;            // arrivals per finalize block
     int fin_slot;            // this job's index in the FinTable
+    int cull;                // 1: skip tiles whose box proves every term flushes to zero
+    const int* perm;         // visit order -> row of the query table (Morton order), or NULL
     signed char cols[SKB_MAXD];
 };
 
@@ -88,6 +95,7 @@ struct FinJob {
     double* out_logp;        // [M] natural log density, or NULL
     double* out_m;           // partial-mode outputs (natural-log m, s) or NULL
     double* out_s;
+    const int* perm;         // visit order -> row (outputs and u are indexed by row), or NULL
     double log_norm;
     double log_wmax;         // partial-mode outputs carry the true weights: m += log(w_max)
     double sign_logjac;      // sign * log|jac|
@@ -113,9 +121,15 @@ struct ScoreLaunch {
 };
 
 // kernels / launchers (defined in the .cu files)
-cudaError_t launch_pack(const void* train, int f32, long long N, int D, long long ld, int is_whitened,
-                        const KdeDev* kde_dev, const double* w, double inv_wmax,
-                        float* tiles, double* zt64, int ntiles, cudaStream_t st);
+cudaError_t launch_fit(const void* train, int f32, long long N, int D, long long ld, int is_whitened,
+                       const KdeDev* kde_dev, double* zt64, cudaStream_t st);
+cudaError_t launch_pack(const double* zt64, const int* perm, int D, double c, const double* w, double inv_wmax,
+                        float* tiles, int ntiles, float* boxes, cudaStream_t st);
+size_t sort_temp_bytes(long long M);
+cudaError_t launch_query_order(const KdeDev* kde, const void* q, int q_f32, long long M, long long ldq,
+                               int q_is_whitened, const signed char* cols_dev, unsigned long long* keys_in,
+                               unsigned long long* keys_out, int* idx_in, int* idx_out, void* temp, size_t temp_bytes,
+                               cudaStream_t st);
 cudaError_t launch_score(int D, bool small_q, const ScoreLaunch& L, int njobs, long long max_qblocks, int max_split,
                          cudaStream_t st);
 int score_ctas_per_sm(int D, bool small_q);

@@ -81,12 +81,14 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// diagnostics: [0] overflow re-runs of a 64-point block (warp level), [1] blocks processed (warp level)
+// diagnostics (warp level): [0] overflow re-runs of a 64-point block, [1] 64-point blocks processed,
+// [2] tiles culled by the box test, [3] tiles visited
 __device__ unsigned long long g_stats[4];
 
 constexpr float OVERFLOW_LIMIT = 1.329228e36f;    // 2^120: a block partial sum at/above this is re-run
 constexpr float REF_BIAS = 90.f;                  // reference sits this many binades below the closest point seen
 constexpr int SUB = 64;                           // points per overflow-checked block
+constexpr float CULL_MARGIN = 128.f;              // box lower bound this far past the reference => all terms flush to 0
 
 // ---------------------------------------------------------------------------------------------
 // One pass of a thread's Q queries over (part of) a shared-memory tile.
@@ -278,13 +280,16 @@ __device__ __forceinline__ void merge_partials(const double2* __restrict__ parti
 constexpr double LN2 = 0.693147180559945309417232121458;
 
 __device__ __forceinline__ void finalize_query(const FinTable& fin, int first, int count,
-                                               long long M, long long r)
+                                               long long M, long long v)
 {
+    // v: visit-order position (partials);  r: row of the query table (outputs, uniforms)
+    const int* perm = fin.fj[first].perm;
+    const long long r = perm ? perm[v] : v;
     double log_ratio = -fin.log_m;
     for (int f = first; f < first + count; f++) {
         const FinJob& fj = fin.fj[f];
         double mstar, S;
-        merge_partials(fj.partial, fj.nsplit, M, r, mstar, S);
+        merge_partials(fj.partial, fj.nsplit, M, v, mstar, S);
         if (fj.out_m) { fj.out_m[r] = fj.log_wmax - mstar * LN2; fj.out_s[r] = S; }
         const double lp = fj.log_norm + log(S) - mstar * LN2;
         if (fj.out_logp) fj.out_logp[r] = lp;
@@ -353,8 +358,9 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
         const double c = kde->c;
 #pragma unroll
         for (int q = 0; q < Q; q++) {
-            long long r = qbase + (long long)q * NT + tid;
+            long long r = qbase + (long long)tid * Q + q;   // a warp owns 32*Q consecutive rows of the visit order
             if (r >= M) r = M - 1;                      // clamp: duplicates are computed, never stored
+            if (job.perm) r = job.perm[r];
             double x[D];
             if (job.q_f32) {
                 const float* row = reinterpret_cast<const float*>(job.q) + r * job.ldq;
@@ -412,9 +418,73 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
     for (int q = 0; q < Q; q++) { mref[q] = 0.f; S[q] = 0.0; nm2[q] = pk(0.f, 0.f); }
 
     const int lane = tid & 31;
-    unsigned n_rerun = 0, n_blocks = 0;
-    const int pilot_points = ntl >= 32 ? TN : 64;
-    bool have_ref = false;
+    unsigned n_rerun = 0, n_blocks = 0, n_culled = 0;
+
+    // Reference exponents, per query and independent of split / batch / GPU:
+    //  (1) walk the box table: the farthest corner of a box bounds the distance to every point in it, so
+    //      the min over tiles of that bound is an upper bound of the true minimum; remember the tile whose
+    //      box is nearest ("home" tile);
+    //  (2) evaluate the home tile exactly (min-only, straight from L2): usually the true nearest
+    //      neighbour lives there, which makes the reference tight from the first tile on — tight references
+    //      are what lets the box test cull.
+    float bmin[Q];          // running estimate of the smallest acc seen (absolute), tightened from block sums
+    {
+        const float* __restrict__ bx = kde->boxes;
+        float lbbest[Q];
+        int tbest[Q];
+#pragma unroll
+        for (int q = 0; q < Q; q++) { bmin[q] = INFINITY; lbbest[q] = INFINITY; tbest[q] = 0; }
+#pragma unroll 1
+        for (int t = 0; t < ntiles; t++) {
+            float lo[D], hi[D];
+#pragma unroll
+            for (int k = 0; k < D; k++) { lo[k] = __ldg(bx + (size_t)t * 2 * D + k); hi[k] = __ldg(bx + (size_t)t * 2 * D + D + k); }
+            if (!(lo[0] <= hi[0])) continue;                         // tile without weight
+#pragma unroll
+            for (int q = 0; q < Q; q++) {
+                float ub = 0.f, lb = 0.f;
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    float zq, dup; upk(q2[q][k], zq, dup);
+                    const float a = zq - lo[k], c = zq - hi[k];
+                    const float far = fmaxf(fabsf(a), fabsf(c));
+                    const float gap = fmaxf(fmaxf(-a, c), 0.f);
+                    ub = fmaf(far, far, ub);
+                    lb = fmaf(gap, gap, lb);
+                }
+                bmin[q] = fminf(bmin[q], ub);
+                if (lb < lbbest[q]) { lbbest[q] = lb; tbest[q] = t; }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const float* __restrict__ ht = kde->tiles + (size_t)tbest[q] * STAGE_FLOATS;
+            float zq[D];
+#pragma unroll
+            for (int k = 0; k < D; k++) { float dup; upk(q2[q][k], zq[k], dup); }
+            float best = INFINITY;
+#pragma unroll 1
+            for (int j = 0; j < TN; j += 4) {
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(ht + k * TN + j));
+                    const float d0 = zq[k] - v.x, d1 = zq[k] - v.y, d2 = zq[k] - v.z, d3 = zq[k] - v.w;
+                    a0 = fmaf(d0, d0, a0); a1 = fmaf(d1, d1, a1); a2 = fmaf(d2, d2, a2); a3 = fmaf(d3, d3, a3);
+                }
+                best = fminf(best, fminf(fminf(a0, a1), fminf(a2, a3)));
+            }
+            bmin[q] = fminf(bmin[q], best);
+        }
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            if (!(fabsf(bmin[q]) < 1.0e30f)) bmin[q] = REF_BIAS;     // inf/NaN rows: keep a finite reference
+            const float m = floorf(bmin[q]) - REF_BIAS;
+            mref[q] = m;
+            nm2[q] = pk(-m, -m);
+        }
+    }
+
     for (int it = 0; it < ntl; it++) {
         const int s = it % NSTAGE;
         const uint32_t ph = (it / NSTAGE) & 1;
@@ -432,34 +502,29 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
 
         u64 sum2[Q];
         float amin[Q];
-        if (!have_ref) {
-            // pilot: a min-only pass fixes the first reference exponent of each query.  Padding /
-            // zero-weight points sit at PAD_COORD, so a range holding only those is recognised by its
-            // (query independent) huge minimum and skipped.
-#pragma unroll
-            for (int q = 0; q < Q; q++) amin[q] = INFINITY;
-            tile_pass<D, Q, true>(tile, pilot_points, q2, nm2, sum2, amin);
-            bool only_pad = true;
-#pragma unroll
-            for (int q = 0; q < Q; q++) only_pad &= !(amin[q] < 1.0e30f);
-            if (pilot_points < TN && __all_sync(0xffffffffu, only_pad)) {
-                tile_pass<D, Q, true>(tile, TN, q2, nm2, sum2, amin);
-                only_pad = true;
-#pragma unroll
-                for (int q = 0; q < Q; q++) only_pad &= !(amin[q] < 1.0e30f);
-            }
-            if (__all_sync(0xffffffffu, only_pad)) {     // the whole tile carries no weight
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_bar[s]);
-                continue;
-            }
-            have_ref = true;
+        // cull: if for every query of this warp the nearest point of the tile's box is more than 127
+        // binades beyond the reference, every term 2^(m - acc) of the tile flushes to zero in fp32 — the
+        // tile contributes exactly nothing and is skipped (warp uniform; other queries' boxes never change
+        // a query's own arithmetic).
+        if (job.cull) {
+            const float* hdr = tile + (D + 1) * TN;
+            bool skip = true;
 #pragma unroll
             for (int q = 0; q < Q; q++) {
-                float m = floorf(amin[q]) - REF_BIAS;
-                if (!(fabsf(m) < 1.0e30f)) m = 0.f;      // inf/NaN rows: keep a finite reference
-                mref[q] = m;
-                nm2[q] = pk(-m, -m);
+                float lb = 0.f;
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    float zq, dup; upk(q2[q][k], zq, dup);
+                    const float gap = fmaxf(fmaxf(hdr[k] - zq, zq - hdr[D + k]), 0.f);
+                    lb = fmaf(gap, gap, lb);
+                }
+                skip &= (lb - mref[q] > CULL_MARGIN);
+            }
+            if (__all_sync(0xffffffffu, skip)) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[s]);
+                n_culled++;
+                continue;
             }
         }
 #pragma unroll 1
@@ -480,7 +545,13 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
                 }
                 if (!__any_sync(0xffffffffu, bad)) {
 #pragma unroll
-                    for (int q = 0; q < Q; q++) S[q] += (double)ts[q];
+                    for (int q = 0; q < Q; q++) {
+                        S[q] += (double)ts[q];
+                        // ts >= its largest term 2^(m - acc_min): the exponent of the block sum bounds the
+                        // closest point of the block to within the block size
+                        if (ts[q] > 0.f)
+                            bmin[q] = fminf(bmin[q], mref[q] - (float)((__float_as_int(ts[q]) >> 23) - 127));
+                    }
                     break;
                 }
                 // rare: a query met a point far closer than its window allows -> recentre, re-run block
@@ -495,6 +566,7 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
                         const float delta = floorf(amin[q]) - REF_BIAS;   // new reference relative to mref
                         if (delta < 0.f && delta > -1.0e30f) {
                             fixable = true;
+                            bmin[q] = fminf(bmin[q], mref[q] + floorf(amin[q]));
                             mref[q] += delta;
                             nm2[q] = pk(-mref[q], -mref[q]);
                             double e = (double)delta;
@@ -512,6 +584,17 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
                 }
             }
         }
+        // move the reference down when the sums have shown a closer point than it was built for (exact:
+        // S is rescaled by a power of two); a tighter reference culls more of the tiles still to come
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const float want = floorf(bmin[q]) - REF_BIAS;
+            if (mref[q] - want >= 8.f) {
+                S[q] = ldexp(S[q], (int)fmaxf(want - mref[q], -4000.f));
+                mref[q] = want;
+                nm2[q] = pk(-want, -want);
+            }
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
@@ -519,6 +602,8 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
     if (lane == 0) {
         if (n_rerun) atomicAdd(&g_stats[0], (unsigned long long)n_rerun);
         atomicAdd(&g_stats[1], (unsigned long long)n_blocks);
+        atomicAdd(&g_stats[2], (unsigned long long)n_culled);
+        atomicAdd(&g_stats[3], (unsigned long long)ntl);
     }
 
     // ---- epilogue ------------------------------------------------------------------------------
@@ -527,18 +612,20 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
         // single split, ungrouped: finalize straight from registers
 #pragma unroll
         for (int q = 0; q < Q; q++) {
-            const long long r = qbase + (long long)q * NT + tid;
-            if (r < M) {
+            const long long v = qbase + (long long)tid * Q + q;          // position in the visit order
+            if (v < M) {
+                const long long r = job.perm ? job.perm[v] : v;          // row of the query table
                 if (myfin.out_m) { myfin.out_m[r] = myfin.log_wmax - (double)mref[q] * LN2; myfin.out_s[r] = S[q]; }
                 if (myfin.out_logp) myfin.out_logp[r] = myfin.log_norm + log(S[q]) - (double)mref[q] * LN2;
             }
         }
         return;
     }
+    // partial states and arrival counters are indexed by visit-order position (shared by a group)
 #pragma unroll
     for (int q = 0; q < Q; q++) {
-        const long long r = qbase + (long long)q * NT + tid;
-        if (r < M) myfin.partial[(long long)blockIdx.z * M + r] = make_double2((double)mref[q], S[q]);
+        const long long v = qbase + (long long)tid * Q + q;
+        if (v < M) myfin.partial[(long long)blockIdx.z * M + v] = make_double2((double)mref[q], S[q]);
     }
     // last-arriving CTA of each finalize block (FB queries) merges splits / forms the ratio + accept
     __threadfence();
@@ -563,62 +650,6 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
             if (r < M) finalize_query(L.fin, job.fin_first, job.fin_count, M, r);
         }
     }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Tile packing (skb_create): whiten (if raw), prescale, cast, transpose into [tile][D+1][TN].
-// ---------------------------------------------------------------------------------------------
-__global__ void skb_pack_kernel(const void* __restrict__ train, int f32, long long N, int D, long long ld,
-                                int is_whitened, const KdeDev* __restrict__ kde,
-                                const double* __restrict__ w, double inv_wmax,
-                                float* __restrict__ tiles, double* __restrict__ zt64, int ntiles)
-{
-    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= (long long)ntiles * TN) return;
-    const long long t = j / TN;
-    const int o = (int)(j % TN);
-    float* dst = tiles + (size_t)t * (D + 1) * TN + o;
-    if (j >= N) {
-        for (int k = 0; k < D; k++) dst[k * TN] = PAD_COORD;
-        dst[D * TN] = 0.f;
-        return;
-    }
-    double x[SKB_MAXD], z[SKB_MAXD];
-    for (int i = 0; i < D; i++)
-        x[i] = f32 ? (double)reinterpret_cast<const float*>(train)[j * ld + i]
-                   : reinterpret_cast<const double*>(train)[j * ld + i];
-    if (is_whitened) {
-        for (int k = 0; k < D; k++) z[k] = x[k];
-    } else {
-        // z = (x - mu) . W  in fp64;  Wc = W * c  ->  z = ((x - mu) . Wc) / c
-        for (int i = 0; i < D; i++) x[i] -= kde->mu[i];
-        for (int k = 0; k < D; k++) {
-            double a = 0.0;
-            for (int i = 0; i < D; i++) a = fma(x[i], kde->Wc[i * D + k], a);
-            z[k] = a / kde->c;
-        }
-    }
-    for (int k = 0; k < D; k++) zt64[j * D + k] = z[k];
-    const double wj = w ? w[j] : 1.0;
-    if (wj > 0.0) {
-        for (int k = 0; k < D; k++) dst[k * TN] = (float)(z[k] * kde->c);
-        dst[D * TN] = (float)(wj * inv_wmax);
-    } else {
-        for (int k = 0; k < D; k++) dst[k * TN] = PAD_COORD;
-        dst[D * TN] = 0.f;
-    }
-}
-
-cudaError_t launch_pack(const void* train, int f32, long long N, int D, long long ld, int is_whitened,
-                        const KdeDev* kde_dev, const double* w, double inv_wmax,
-                        float* tiles, double* zt64, int ntiles, cudaStream_t st)
-{
-    const long long total = (long long)ntiles * TN;
-    const int bs = 256;
-    skb_pack_kernel<<<(unsigned)((total + bs - 1) / bs), bs, 0, st>>>(train, f32, N, D, ld, is_whitened, kde_dev,
-                                                                      w, inv_wmax, tiles, zt64, ntiles);
-    count_launch();
-    return cudaGetLastError();
 }
 
 template <int D, int Q>
