@@ -301,6 +301,7 @@ def run_ours(args):
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = lib.skb_launch_count()
+    lib.skb_debug_counters(local, (C.c_uint64 * 4)(), 1)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -349,7 +350,23 @@ def run_ours(args):
     h2d = args.batch * D * 8 + args.batch * 8
     d2h = args.batch + 8
 
-    # ---- roofline of the dominant kernel (skb_score_kernel<8>), peaks measured live on this GPU ----
+    # ---- the same kernel with culling off (every pair evaluated): the FMA-pipe efficiency of the arithmetic ----
+    dense_ms = None
+    if rank == 0:
+        os.environ["SKB_NO_CULL"] = "1"
+        sampler.score_accept(*batch(0))
+        torch.cuda.synchronize()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for i in range(2):
+            sampler.score_accept(*batch(1 + i))
+        d1.record()
+        torch.cuda.synchronize()
+        dense_ms = d0.elapsed_time(d1) / 2.0
+        os.environ.pop("SKB_NO_CULL", None)
+        lib.skb_debug_counters(local, (C.c_uint64 * 4)(), 1)
+
+    # ---- roofline of the dominant kernel (skb_score_kernel<8,4>), peaks measured live on this GPU ----
     roof = None
     if rank == 0:
         fma, ex2 = C.c_double(), C.c_double()
@@ -366,22 +383,34 @@ def run_ours(args):
             except Exception:
                 traffic = None
         flop_pair = 3 * D + 1
+        # executed pairs: 64-point blocks actually evaluated (warp level) x 64 points x 32 lanes x Q queries
+        q_per_thread = 4
+        exec_pairs_per_launch = st[1] * 64.0 * 32.0 * q_per_thread / max(args.steps, 1)
+        exec_frac = exec_pairs_per_launch / pairs_per_step_rank
+        ach_exec = exec_pairs_per_launch / (kernel_ms * 1e-3)
+        dense_rate = pairs_per_step_rank / (dense_ms * 1e-3)
         roof = {
             # bound: the FP32 FMA pipe (with the SFU as second limit) — not HBM, not tensor cores
             "bound": "fp32", "kernel": "skb::skb_score_kernel<8,4>",
             "achieved": ach * flop_pair / 1e12, "peak": peak_pairs * flop_pair / 1e12, "unit": "TFLOP/s",
             "frac": ach / peak_pairs, "traffic": traffic,
-            "definition": "achieved = pairs/launch x (3d+1) algorithmic FP32 FLOP / CUDA-event launch time; "
-                          "peak = min(FFMA lane-ops/s / (2d+1), EX2/s) x (3d+1): the pair roofline of SURVEY.md "
-                          "§8d expressed in FLOP/s (a pair costs 2d+1 FMA-pipe lane ops, 3d+1 FLOP, 1 EX2)",
+            "definition": "achieved = ALGORITHMIC work: pairs/launch x (3d+1) FP32 FLOP / CUDA-event launch time, "
+                          "every (query, training) pair counted; peak = min(FFMA lane-ops/s / (2d+1), EX2/s) x (3d+1), "
+                          "the pair roofline of SURVEY.md §8d in FLOP/s.  frac > 1 is expected: tiles whose box test "
+                          "proves that every pair term flushes to zero in fp32 are skipped (executed_pair_fraction); "
+                          "frac_executed and frac_dense give the arithmetic's own pipe efficiency",
+            "executed_pair_fraction": exec_frac,
+            "frac_executed": ach_exec / peak_pairs,
+            "frac_dense": dense_rate / peak_pairs, "dense_ms_per_launch": dense_ms,
+            "dense_note": "same launch with SKB_NO_CULL=1 (all pairs evaluated), 2 launches after the timed region",
             "achieved_gpairs": ach / 1e9, "peak_gpairs": peak_pairs / 1e9,
             "fp32_fma_peak_tflops_measured": 2.0 * fma.value / 1e12, "ex2_peak_per_s_measured": ex2.value,
-            "frac_of_raw_fp32_flops": ach * flop_pair / (2.0 * fma.value),
             "peak_source": "measured live on this GPU by skb_measure_pipes (FFMA2 and MUFU.EX2 saturation loops, "
                            "300 ms each); MEASURED_PEAKS.json holds only HBM and bf16-tensor figures",
             "kernel_ms_per_launch": kernel_ms, "pairs_per_launch": pairs_per_step_rank,
             "hbm_gbs_peak_for_reference": _hbm_peak(),
             "rerun_blocks_frac": (st[0] / float(st[1])) if st[1] else None,
+            "tiles_culled_frac": (st[2] / float(st[3])) if st[3] else None,
         }
 
     line = None

@@ -124,11 +124,9 @@ static void kd_order(const float* z, int D, int* idx, long long n)
 
 // ---- launch planning --------------------------------------------------------------------------
 
-// Training-set splits of a launch.  The count depends on the fitted KDE ONLY (never on the number of
-// query rows), so the arithmetic a query sees — split boundaries, pilot tile, exponent-reference
-// history — is the same whatever batch, chunk or GPU it lands in: results are bit-identical under any
-// query sharding.  >= 128 tiles per split keeps the per-split pilot pass under 1 % (measured: 8 splits
-// cost 0.8 % against 1 on the bench workload, 32 cost 7 %).
+// Training-set splits of a launch (blockIdx.z).  Never a function of the number of query rows: the
+// arithmetic a query sees must be the same whatever batch, chunk or GPU it lands in, so that results
+// are bit-identical under any query sharding.
 static bool cull_enabled()
 {
     const char* e = getenv("SKB_NO_CULL");       // SKB_NO_CULL=1: evaluate every pair (roofline measurements)
@@ -137,17 +135,14 @@ static bool cull_enabled()
 
 static int plan_nsplit(const skb_kde* h, long long /*M*/, int /*njobs*/)
 {
-    if (const char* f = getenv("SKB_FORCE_NSPLIT")) {
+    if (const char* f = getenv("SKB_FORCE_NSPLIT")) {      // experiments only
         int v = atoi(f);
         if (v >= 1) return v > h->hk.ntiles ? h->hk.ntiles : v;
     }
-    // with tile culling every CTA walks the box table of ALL tiles once; splitting the tiles over CTAs
-    // would repeat that walk per split, so the culled path never splits
-    if (cull_enabled()) return 1;
-    int ns = h->hk.ntiles / 128;
-    if (ns < 1) ns = 1;
-    if (ns > 8) ns = 8;
-    return ns;
+    // Every CTA walks the box table of ALL tiles once to find its queries' exponent references; splitting
+    // the tiles over CTAs would repeat that walk per split, and with culling a CTA only visits a fraction
+    // of the tiles anyway.  One split also keeps a query's arithmetic a function of the fitted KDE alone.
+    return 1;
 }
 
 struct GroupSpec {

@@ -17,9 +17,15 @@ typedef unsigned long long u64;
 // Tiles are the leaves of a kd-tree over the training points (built on the host at fit time), so a
 // tile is spatially compact and its box test can prove that every pair term flushes to zero.
 constexpr int TN = 256;              // training points per tile
-constexpr int NSTAGE = 4;            // TMA ring depth
-constexpr int NT = 128;              // threads per CTA of the score kernel
-constexpr int FB = 128;              // queries per finalize block (arrival-counter granularity)
+#ifndef SKB_NSTAGE
+#define SKB_NSTAGE 4
+#endif
+constexpr int NSTAGE = SKB_NSTAGE;   // TMA ring depth
+#ifndef SKB_NT
+#define SKB_NT 128
+#endif
+constexpr int NT = SKB_NT;           // threads per CTA of the score kernel
+constexpr int FB = 64;               // queries per finalize block (arrival-counter granularity)
 constexpr float PAD_COORD = 1.0e18f; // coordinate of padding / zero-weight points: exp2(-1e36) == 0
 
 #ifndef SKB_Q_LE2

@@ -309,7 +309,7 @@ __device__ __forceinline__ void finalize_query(const FinTable& fin, int first, i
 // The score kernel.  grid = (query blocks, jobs, training splits), block = NT threads.
 // ---------------------------------------------------------------------------------------------
 template <int D, int Q>
-__global__ void __launch_bounds__(NT, (Q == queries_per_thread(D) ? min_blocks_per_sm(D) : 4))
+__global__ void __launch_bounds__(NT, (Q == queries_per_thread(D) ? min_blocks_per_sm(D) : 4) * (128 / NT))
 skb_score_kernel(const __grid_constant__ ScoreLaunch L)
 {
     constexpr int QB = NT * Q;
