@@ -25,7 +25,7 @@ constexpr int NSTAGE = SKB_NSTAGE;   // TMA ring depth
 #define SKB_NT 128
 #endif
 constexpr int NT = SKB_NT;           // threads per CTA of the score kernel
-constexpr int FB = 64;               // queries per finalize block (arrival-counter granularity)
+constexpr int FB = 32;               // queries per finalize block (arrival-counter granularity)
 constexpr float PAD_COORD = 1.0e18f; // coordinate of padding / zero-weight points: exp2(-1e36) == 0
 
 #ifndef SKB_Q_LE2
@@ -137,7 +137,7 @@ cudaError_t launch_query_order(const KdeDev* kde, const void* q, int q_f32, long
                                unsigned long long* keys_out, int* idx_in, int* idx_out, void* temp, size_t temp_bytes,
                                cudaStream_t st);
 cudaError_t launch_score(int D, bool small_q, const ScoreLaunch& L, int njobs, long long max_qblocks, int max_split,
-                         cudaStream_t st);
+                         int max_ntiles, cudaStream_t st);
 int score_ctas_per_sm(int D, bool small_q);
 cudaError_t launch_draw(const KdeDev* kde, int D, long long M, const double* u, const double* z,
                         uint64_t seed, uint64_t offset, const long long* rows,

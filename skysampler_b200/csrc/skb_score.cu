@@ -326,6 +326,7 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
     float* stages = reinterpret_cast<float*>(smem_raw);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NSTAGE * STAGE_BYTES);
     uint64_t* empty_bar = full_bar + NSTAGE;
+    unsigned* need_bits = reinterpret_cast<unsigned*>(empty_bar + NSTAGE);   // one bit per tile: some warp needs it
     __shared__ int s_last[QB / FB];
 
     const int tid = threadIdx.x;
@@ -342,15 +343,9 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
         for (int s = 0; s < NSTAGE; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NWARP); }
         mbar_fence_init();
     }
+    const int nwords = (ntl + 31) >> 5;
+    for (int w = tid; w < nwords; w += NT) need_bits[w] = 0u;
     __syncthreads();
-    if (tid == 0) {
-        const int npre = ntl < NSTAGE ? ntl : NSTAGE;
-        for (int s = 0; s < npre; s++) {
-            mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-            tma_bulk_g2s(stages + (size_t)s * STAGE_FLOATS, gtiles + (size_t)s * STAGE_FLOATS, STAGE_BYTES,
-                         &full_bar[s]);
-        }
-    }
 
     // ---- prologue: load this thread's Q query rows, whiten + prescale in fp64, pack as {z, z} ----
     u64 q2[Q][D];
@@ -418,7 +413,7 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
     for (int q = 0; q < Q; q++) { mref[q] = 0.f; S[q] = 0.0; nm2[q] = pk(0.f, 0.f); }
 
     const int lane = tid & 31;
-    unsigned n_rerun = 0, n_blocks = 0, n_culled = 0;
+    unsigned n_rerun = 0, n_blocks = 0, n_culled = 0, n_visited = 0;
 
     // Reference exponents, per query and independent of split / batch / GPU:
     //  (1) walk the box table: the farthest corner of a box bounds the distance to every point in it, so
@@ -485,16 +480,81 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
         }
     }
 
-    for (int it = 0; it < ntl; it++) {
+    // ---- which tiles does this CTA need at all?  A tile that every warp can already cull with its initial
+    // references is never requested from L2 (references only move down, so this is conservative).
+    if (job.cull) {
+        const float* __restrict__ bx = kde->boxes + (size_t)t0 * 2 * D;
+#pragma unroll 1
+        for (int w = 0; w < nwords; w++) {
+            unsigned word = 0u;
+            const int tend = (ntl - w * 32) < 32 ? (ntl - w * 32) : 32;
+#pragma unroll 1
+            for (int b = 0; b < tend; b++) {
+                const int t = w * 32 + b;
+                float lo[D], hi[D];
+#pragma unroll
+                for (int k = 0; k < D; k++) { lo[k] = __ldg(bx + (size_t)t * 2 * D + k); hi[k] = __ldg(bx + (size_t)t * 2 * D + D + k); }
+                bool need = false;
+#pragma unroll
+                for (int q = 0; q < Q; q++) {
+                    float lb = 0.f;
+#pragma unroll
+                    for (int k = 0; k < D; k++) {
+                        float zq, dup; upk(q2[q][k], zq, dup);
+                        const float gap = fmaxf(fmaxf(lo[k] - zq, zq - hi[k]), 0.f);
+                        lb = fmaf(gap, gap, lb);
+                    }
+                    need |= !(lb - mref[q] > CULL_MARGIN);           // (NaN / empty box compare false -> handled below)
+                }
+                if (!(lo[0] <= hi[0])) need = false;                  // tile without weight
+                if (__any_sync(0xffffffffu, need)) word |= 1u << b;
+            }
+            if (lane == 0 && word) atomicOr(&need_bits[w], word);
+        }
+    } else {
+        for (int w = tid; w < nwords; w += NT) {
+            const int rem = ntl - w * 32;
+            need_bits[w] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+        }
+    }
+    __syncthreads();
+
+    // cursors over the set bits: cc = tile this warp consumes next, pc (thread 0) = tile to request next
+    int cw = -1, pw = -1;
+    unsigned cbits = 0u, pbits = 0u;
+    auto next_tile = [&](int& w, unsigned& bits) -> int {
+        while (bits == 0u) {
+            if (++w >= nwords) return -1;
+            bits = need_bits[w];
+        }
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1u;
+        return w * 32 + b;
+    };
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; s++) {
+            const int t = next_tile(pw, pbits);
+            if (t < 0) break;
+            mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+            tma_bulk_g2s(stages + (size_t)s * STAGE_FLOATS, gtiles + (size_t)t * STAGE_FLOATS, STAGE_BYTES, &full_bar[s]);
+        }
+    }
+
+    for (int it = 0;; it++) {
+        if (next_tile(cw, cbits) < 0) break;
+        n_visited++;
         const int s = it % NSTAGE;
         const uint32_t ph = (it / NSTAGE) & 1;
         // producer: once every warp has released the stage of the previous tile, refill it
-        if (tid == 0 && it >= 1 && it - 1 + NSTAGE < ntl) {
-            const int sp = (it - 1) % NSTAGE;
-            mbar_wait(&empty_bar[sp], ((it - 1) / NSTAGE) & 1);
-            mbar_expect_tx(&full_bar[sp], STAGE_BYTES);
-            tma_bulk_g2s(stages + (size_t)sp * STAGE_FLOATS, gtiles + (size_t)(it - 1 + NSTAGE) * STAGE_FLOATS,
-                         STAGE_BYTES, &full_bar[sp]);
+        if (tid == 0 && it >= 1) {
+            const int t = next_tile(pw, pbits);
+            if (t >= 0) {
+                const int sp = (it - 1) % NSTAGE;
+                mbar_wait(&empty_bar[sp], ((it - 1) / NSTAGE) & 1);
+                mbar_expect_tx(&full_bar[sp], STAGE_BYTES);
+                tma_bulk_g2s(stages + (size_t)sp * STAGE_FLOATS, gtiles + (size_t)t * STAGE_FLOATS, STAGE_BYTES,
+                             &full_bar[sp]);
+            }
         }
         __syncwarp();
         mbar_wait(&full_bar[s], ph);
@@ -602,8 +662,8 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
     if (lane == 0) {
         if (n_rerun) atomicAdd(&g_stats[0], (unsigned long long)n_rerun);
         atomicAdd(&g_stats[1], (unsigned long long)n_blocks);
-        atomicAdd(&g_stats[2], (unsigned long long)n_culled);
-        atomicAdd(&g_stats[3], (unsigned long long)ntl);
+        atomicAdd(&g_stats[2], (unsigned long long)(n_culled + (unsigned)ntl - n_visited));
+        atomicAdd(&g_stats[3], (unsigned long long)ntl);      // tiles of the split (culled = box-culled at either level)
     }
 
     // ---- epilogue ------------------------------------------------------------------------------
@@ -654,9 +714,10 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
 
 template <int D, int Q>
 static cudaError_t launch_score_dq(const ScoreLaunch& L, int njobs, long long max_qblocks, int max_split,
-                                   cudaStream_t st)
+                                   int max_ntiles, cudaStream_t st)
 {
-    const size_t smem = (size_t)NSTAGE * stage_floats(D) * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t);
+    const size_t smem = (size_t)NSTAGE * stage_floats(D) * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t) +
+                        (((size_t)max_ntiles + 31) / 32) * 4 + 16;
     cudaError_t e = cudaFuncSetAttribute(skb_score_kernel<D, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)max_qblocks, (unsigned)njobs, (unsigned)max_split);
@@ -708,11 +769,11 @@ int score_ctas_per_sm(int D, bool small_q)
 static_assert(sizeof(ScoreLaunch) <= 4000, "ScoreLaunch must fit the classic 4 KB kernel-parameter space");
 
 cudaError_t launch_score(int D, bool small_q, const ScoreLaunch& L, int njobs, long long max_qblocks, int max_split,
-                         cudaStream_t st)
+                         int max_ntiles, cudaStream_t st)
 {
     switch (D) {
-#define SKB_CASE(d) case d: return small_q ? launch_score_dq<d, queries_per_thread_small(d)>(L, njobs, max_qblocks, max_split, st) \
-                                           : launch_score_dq<d, queries_per_thread(d)>(L, njobs, max_qblocks, max_split, st);
+#define SKB_CASE(d) case d: return small_q ? launch_score_dq<d, queries_per_thread_small(d)>(L, njobs, max_qblocks, max_split, max_ntiles, st) \
+                                           : launch_score_dq<d, queries_per_thread(d)>(L, njobs, max_qblocks, max_split, max_ntiles, st);
         SKB_CASE(1) SKB_CASE(2) SKB_CASE(3) SKB_CASE(4) SKB_CASE(5) SKB_CASE(6) SKB_CASE(7) SKB_CASE(8)
         SKB_CASE(9) SKB_CASE(10) SKB_CASE(11) SKB_CASE(12) SKB_CASE(13) SKB_CASE(14) SKB_CASE(15) SKB_CASE(16)
 #undef SKB_CASE
