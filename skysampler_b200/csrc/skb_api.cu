@@ -77,6 +77,7 @@ struct skb_kde {
     KdeDev* dk = nullptr;      // device descriptor
     float* tiles = nullptr;
     float* boxes = nullptr;
+    float* sboxes = nullptr;
     int* perm = nullptr;       // fit-time only
     double* zt64 = nullptr;
     double* cumsum = nullptr;
@@ -102,7 +103,7 @@ struct DeviceGuard {
 
 // ---- kd-tree ordering (host, fit time) ----------------------------------------------------------
 // Recursive median split along the widest coordinate; the left part always takes a whole number of
-// tiles so that every tile except the last is a full leaf of TN points.
+// tiles (of super-boxes higher up) so that every tile except the last is a full leaf of TN points.
 static void kd_order(const float* z, int D, int* idx, long long n)
 {
     if (n <= TN) return;
@@ -114,8 +115,11 @@ static void kd_order(const float* z, int D, int* idx, long long n)
     }
     int kbest = 0;
     for (int k = 1; k < D; k++) if (hi[k] - lo[k] > hi[kbest] - lo[kbest]) kbest = k;
-    const long long ntile = (n + TN - 1) / TN;
-    const long long nl = ((ntile + 1) / 2) * TN;          // 0 < nl < n because n > TN
+    // split in whole super-boxes (SG tiles) while the node is larger than one, then in whole tiles: every
+    // aligned run of SG tiles is then a kd subtree, so its union box is as tight as the tree allows
+    const long long unit = n > (long long)SG * TN ? (long long)SG * TN : TN;
+    const long long nunit = (n + unit - 1) / unit;
+    const long long nl = ((nunit + 1) / 2) * unit;        // 0 < nl < n because nunit >= 2
     std::nth_element(idx, idx + nl, idx + n,
                      [z, D, kbest](int a, int b) { return z[(size_t)a * D + kbest] < z[(size_t)b * D + kbest]; });
     kd_order(z, D, idx, nl);
@@ -479,9 +483,12 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
     const size_t tile_bytes = (size_t)hk.ntiles * stage_floats(d) * sizeof(float);
     SKB_CUDA_C(cudaMalloc(&k->tiles, tile_bytes));
     SKB_CUDA_C(cudaMalloc(&k->boxes, (size_t)hk.ntiles * 2 * d * sizeof(float)));
-    SKB_CUDA_C(launch_pack(k->zt64, k->perm, d, hk.c, d_w, 1.0 / wmax, k->tiles, hk.ntiles, k->boxes, 0));
+    hk.nsuper = (hk.ntiles + SG - 1) / SG;
+    SKB_CUDA_C(cudaMalloc(&k->sboxes, (size_t)hk.nsuper * 2 * d * sizeof(float)));
+    SKB_CUDA_C(launch_pack(k->zt64, k->perm, d, hk.c, d_w, 1.0 / wmax, k->tiles, hk.ntiles, k->boxes, k->sboxes, 0));
     hk.tiles = k->tiles;
     hk.boxes = k->boxes;
+    hk.sboxes = k->sboxes;
     SKB_CUDA_C(cudaMemcpy(k->dk, &hk, sizeof(KdeDev), cudaMemcpyHostToDevice));
     SKB_CUDA_C(cudaStreamSynchronize(0));
     cudaFree(k->perm);
@@ -500,6 +507,7 @@ int skb_destroy(skb_handle h)
     cudaDeviceSynchronize();
     if (h->tiles) cudaFree(h->tiles);
     if (h->boxes) cudaFree(h->boxes);
+    if (h->sboxes) cudaFree(h->sboxes);
     if (h->perm) cudaFree(h->perm);
     if (h->zt64) cudaFree(h->zt64);
     if (h->cumsum) cudaFree(h->cumsum);

@@ -85,6 +85,21 @@ __global__ void skb_box_kernel(float* __restrict__ tiles, const int* __restrict_
     }
 }
 
+// union boxes of SG consecutive tiles: one thread per (super-box, coordinate)
+__global__ void skb_superbox_kernel(const float* __restrict__ boxes, int D, int ntiles, int nsuper, float* __restrict__ sboxes)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsuper * D) return;
+    const int s = i / D, k = i % D;
+    float lo = INFINITY, hi = -INFINITY;
+    for (int t = s * SG; t < ntiles && t < (s + 1) * SG; t++) {
+        const float a = boxes[(size_t)t * 2 * D + k], b = boxes[(size_t)t * 2 * D + D + k];
+        if (a <= b) { lo = fminf(lo, a); hi = fmaxf(hi, b); }
+    }
+    sboxes[(size_t)s * 2 * D + k] = lo;
+    sboxes[(size_t)s * 2 * D + D + k] = hi;
+}
+
 cudaError_t launch_fit(const void* train, int f32, long long N, int D, long long ld, int is_whitened,
                        const KdeDev* kde_dev, double* zt64, cudaStream_t st)
 {
@@ -95,13 +110,15 @@ cudaError_t launch_fit(const void* train, int f32, long long N, int D, long long
 }
 
 cudaError_t launch_pack(const double* zt64, const int* perm, int D, double c, const double* w, double inv_wmax,
-                        float* tiles, int ntiles, float* boxes, cudaStream_t st)
+                        float* tiles, int ntiles, float* boxes, float* sboxes, cudaStream_t st)
 {
     const long long total = (long long)ntiles * TN;
     const int bs = 256;
     skb_pack_kernel<<<(unsigned)((total + bs - 1) / bs), bs, 0, st>>>(zt64, perm, D, c, w, inv_wmax, tiles, ntiles);
     skb_box_kernel<<<(unsigned)((ntiles + 7) / 8), 256, 0, st>>>(tiles, perm, D, ntiles, boxes);
-    count_launch(2);
+    const int nsuper = (ntiles + SG - 1) / SG;
+    skb_superbox_kernel<<<(unsigned)((nsuper * D + 127) / 128), 128, 0, st>>>(boxes, D, ntiles, nsuper, sboxes);
+    count_launch(3);
     return cudaGetLastError();
 }
 
@@ -134,7 +151,7 @@ __global__ void skb_qkey_kernel(const KdeDev* __restrict__ kde, const void* __re
     }
     // Morton interleave of the leading min(D, 8) coordinates, 63 / nd bits each
     const int nd = D < 8 ? D : 8;
-    const int bits = 63 / nd;
+    const int bits = (63 / nd) < 20 ? (63 / nd) : 20;
     const float span = (float)((1u << bits) - 1);
     unsigned cell[8];
     for (int k = 0; k < nd; k++) {

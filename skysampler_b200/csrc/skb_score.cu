@@ -416,47 +416,62 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
     unsigned n_rerun = 0, n_blocks = 0, n_culled = 0, n_visited = 0;
 
     // Reference exponents, per query and independent of split / batch / GPU:
-    //  (1) walk the box table: the farthest corner of a box bounds the distance to every point in it, so
-    //      the min over tiles of that bound is an upper bound of the true minimum; remember the tile whose
-    //      box is nearest ("home" tile);
-    //  (2) evaluate the home tile exactly (min-only, straight from L2): usually the true nearest
-    //      neighbour lives there, which makes the reference tight from the first tile on — tight references
-    //      are what lets the box test cull.
-    float bmin[Q];          // running estimate of the smallest acc seen (absolute), tightened from block sums
+    //  (1) nearest super-box (SG consecutive kd leaves) by box distance, then the nearest tile box inside
+    //      it: the query's "home" tile;
+    //  (2) the home tile is evaluated exactly (min-only, straight from L2).  A real point's distance is an
+    //      upper bound of the true minimum, and the true nearest neighbour usually lives in the home tile,
+    //      so the reference is tight from the first tile on — tight references are what lets the box test
+    //      cull.  (If a closer point turns up later the reference is tightened / recentred on the fly.)
+    float bmin[Q];          // running estimate of the smallest acc seen (absolute)
     {
+        const float* __restrict__ sbx = kde->sboxes;
         const float* __restrict__ bx = kde->boxes;
+        const int nsuper = kde->nsuper;
         float lbbest[Q];
-        int tbest[Q];
+        int sbest[Q];
 #pragma unroll
-        for (int q = 0; q < Q; q++) { bmin[q] = INFINITY; lbbest[q] = INFINITY; tbest[q] = 0; }
+        for (int q = 0; q < Q; q++) { lbbest[q] = INFINITY; sbest[q] = 0; }
 #pragma unroll 1
-        for (int t = 0; t < ntiles; t++) {
+        for (int sidx = 0; sidx < nsuper; sidx++) {
             float lo[D], hi[D];
 #pragma unroll
-            for (int k = 0; k < D; k++) { lo[k] = __ldg(bx + (size_t)t * 2 * D + k); hi[k] = __ldg(bx + (size_t)t * 2 * D + D + k); }
-            if (!(lo[0] <= hi[0])) continue;                         // tile without weight
+            for (int k = 0; k < D; k++) { lo[k] = __ldg(sbx + (size_t)sidx * 2 * D + k); hi[k] = __ldg(sbx + (size_t)sidx * 2 * D + D + k); }
+            if (!(lo[0] <= hi[0])) continue;
 #pragma unroll
             for (int q = 0; q < Q; q++) {
-                float ub = 0.f, lb = 0.f;
+                float lb = 0.f;
 #pragma unroll
                 for (int k = 0; k < D; k++) {
                     float zq, dup; upk(q2[q][k], zq, dup);
-                    const float a = zq - lo[k], c = zq - hi[k];
-                    const float far = fmaxf(fabsf(a), fabsf(c));
-                    const float gap = fmaxf(fmaxf(-a, c), 0.f);
-                    ub = fmaf(far, far, ub);
+                    const float gap = fmaxf(fmaxf(lo[k] - zq, zq - hi[k]), 0.f);
                     lb = fmaf(gap, gap, lb);
                 }
-                bmin[q] = fminf(bmin[q], ub);
-                if (lb < lbbest[q]) { lbbest[q] = lb; tbest[q] = t; }
+                if (lb < lbbest[q]) { lbbest[q] = lb; sbest[q] = sidx; }
             }
         }
 #pragma unroll
         for (int q = 0; q < Q; q++) {
-            const float* __restrict__ ht = kde->tiles + (size_t)tbest[q] * STAGE_FLOATS;
             float zq[D];
 #pragma unroll
             for (int k = 0; k < D; k++) { float dup; upk(q2[q][k], zq[k], dup); }
+            // nearest tile box inside the home super-box
+            int tbest = sbest[q] * SG;
+            float lbt = INFINITY;
+            const int tend = (sbest[q] + 1) * SG < ntiles ? (sbest[q] + 1) * SG : ntiles;
+#pragma unroll 1
+            for (int t = sbest[q] * SG; t < tend; t++) {
+                float lb = 0.f;
+                bool valid = true;
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    const float lo = __ldg(bx + (size_t)t * 2 * D + k), hi = __ldg(bx + (size_t)t * 2 * D + D + k);
+                    valid &= (lo <= hi);
+                    const float gap = fmaxf(fmaxf(lo - zq[k], zq[k] - hi), 0.f);
+                    lb = fmaf(gap, gap, lb);
+                }
+                if (valid && lb < lbt) { lbt = lb; tbest = t; }
+            }
+            const float* __restrict__ ht = kde->tiles + (size_t)tbest * STAGE_FLOATS;
             float best = INFINITY;
 #pragma unroll 1
             for (int j = 0; j < TN; j += 4) {
@@ -469,28 +484,48 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
                 }
                 best = fminf(best, fminf(fminf(a0, a1), fminf(a2, a3)));
             }
-            bmin[q] = fminf(bmin[q], best);
-        }
-#pragma unroll
-        for (int q = 0; q < Q; q++) {
-            if (!(fabsf(bmin[q]) < 1.0e30f)) bmin[q] = REF_BIAS;     // inf/NaN rows: keep a finite reference
-            const float m = floorf(bmin[q]) - REF_BIAS;
+            if (!(best < 1.0e30f)) best = REF_BIAS;                   // inf/NaN rows (or padding only): finite reference
+            bmin[q] = best;
+            const float m = floorf(best) - REF_BIAS;
             mref[q] = m;
             nm2[q] = pk(-m, -m);
         }
     }
 
     // ---- which tiles does this CTA need at all?  A tile that every warp can already cull with its initial
-    // references is never requested from L2 (references only move down, so this is conservative).
+    // references is never requested from L2 (references only move down, so this is conservative).  Two
+    // levels: a super-box that every query of the warp culls dismisses its SG tiles at once.
     if (job.cull) {
-        const float* __restrict__ bx = kde->boxes + (size_t)t0 * 2 * D;
+        const float* __restrict__ sbx = kde->sboxes;
+        const float* __restrict__ bx = kde->boxes;
+        const int s_first = t0 / SG, s_last_ = (t1 + SG - 1) / SG;
 #pragma unroll 1
-        for (int w = 0; w < nwords; w++) {
-            unsigned word = 0u;
-            const int tend = (ntl - w * 32) < 32 ? (ntl - w * 32) : 32;
+        for (int sidx = s_first; sidx < s_last_; sidx++) {
+            bool need_s = false;
+            {
+                float lo[D], hi[D];
+#pragma unroll
+                for (int k = 0; k < D; k++) { lo[k] = __ldg(sbx + (size_t)sidx * 2 * D + k); hi[k] = __ldg(sbx + (size_t)sidx * 2 * D + D + k); }
+#pragma unroll
+                for (int q = 0; q < Q; q++) {
+                    float lb = 0.f;
+#pragma unroll
+                    for (int k = 0; k < D; k++) {
+                        float zq, dup; upk(q2[q][k], zq, dup);
+                        const float gap = fmaxf(fmaxf(lo[k] - zq, zq - hi[k]), 0.f);
+                        lb = fmaf(gap, gap, lb);
+                    }
+                    need_s |= !(lb - mref[q] > CULL_MARGIN);
+                }
+                if (!(lo[0] <= hi[0])) need_s = false;
+            }
+            if (!__any_sync(0xffffffffu, need_s)) continue;
+            unsigned word = 0u;                                        // SG = 16 tiles -> half a bitmap word
+            const int tb = sidx * SG;
 #pragma unroll 1
-            for (int b = 0; b < tend; b++) {
-                const int t = w * 32 + b;
+            for (int b = 0; b < SG; b++) {
+                const int t = tb + b;
+                if (t < t0 || t >= t1) continue;
                 float lo[D], hi[D];
 #pragma unroll
                 for (int k = 0; k < D; k++) { lo[k] = __ldg(bx + (size_t)t * 2 * D + k); hi[k] = __ldg(bx + (size_t)t * 2 * D + D + k); }
@@ -504,12 +539,19 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
                         const float gap = fmaxf(fmaxf(lo[k] - zq, zq - hi[k]), 0.f);
                         lb = fmaf(gap, gap, lb);
                     }
-                    need |= !(lb - mref[q] > CULL_MARGIN);           // (NaN / empty box compare false -> handled below)
+                    need |= !(lb - mref[q] > CULL_MARGIN);
                 }
                 if (!(lo[0] <= hi[0])) need = false;                  // tile without weight
                 if (__any_sync(0xffffffffu, need)) word |= 1u << b;
             }
-            if (lane == 0 && word) atomicOr(&need_bits[w], word);
+            if (lane == 0 && word) {
+                const int rel = tb - t0;                               // bit position of the super-box's first tile
+                if (rel >= 0 && (rel & (SG - 1)) == 0) atomicOr(&need_bits[rel >> 5], word << (rel & 31));
+                else {                                                 // split boundary inside a super-box
+                    for (int b = 0; b < SG; b++)
+                        if ((word >> b) & 1u) { const int r2 = tb + b - t0; atomicOr(&need_bits[r2 >> 5], 1u << (r2 & 31)); }
+                }
+            }
         }
     } else {
         for (int w = tid; w < nwords; w += NT) {
