@@ -340,11 +340,17 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks2 = ClockSampler(local)
+    clocks2.start()
+    time.sleep(0.3)
+    t_e0 = time.time()
     f0.record()
     for i in range(args.steps):
         sampler.step_host(q_host[i % nb_host], u_host[i % nb_host], flags_host)
     f1.record()
     torch.cuda.synchronize()
+    t_e1 = time.time()
+    clk2 = clocks2.stop(t_e0, t_e1)
     e2e_ms = skd.timed_max_ms(f0.elapsed_time(f1), device=dev)
     e2e_value = pairs_per_step_rank * world * args.steps / (e2e_ms * 1e-3)
     h2d = args.batch * D * 8 + args.batch * 8
@@ -425,7 +431,9 @@ def run_ours(args):
             "accept_fraction": accepted / float(args.batch * world * args.steps), "log_m": log_m,
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                    "ms_per_step": e2e_ms / args.steps, "api": "skysampler_b200.pipeline.RatioSampler.step_host"},
+                    "ms_per_step": e2e_ms / args.steps, "api": "skysampler_b200.pipeline.RatioSampler.step_host",
+                    "clocks": clk2},
+            "kernel_ms_each_step": [round(a.elapsed_time(b), 2) for a, b in kev],
             "gpu_launches": int(launches),
             "roofline": roof,
         }
