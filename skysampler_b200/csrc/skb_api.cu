@@ -307,7 +307,8 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
             if (dj.h->hk.ntiles > max_ntiles) max_ntiles = dj.h->hk.ntiles;
         }
         // short query tables: fewer queries per thread -> more CTAs (same bits, see skb_internal.h)
-        const bool small_q = total_rows_splits < 2LL * jobs[j0].h->sms * score_ctas_per_sm(D, false);
+        bool small_q = total_rows_splits < 2LL * jobs[j0].h->sms * score_ctas_per_sm(D, false);
+        if (const char* fq = getenv("SKB_FORCE_SMALLQ")) small_q = atoi(fq) != 0;      // experiments only
         const int QB = NT * (small_q ? queries_per_thread_small(D) : queries_per_thread(D));
         const long long max_qblocks = (max_rows + QB - 1) / QB;
         if (max_qblocks > 0x7fffffffLL) return fail(SKB_EINVAL, "too many query rows for one launch");

@@ -16,13 +16,20 @@ typedef unsigned long long u64;
 // and an LDS.128 of row k yields two packed {x_j, x_j+1} operands for FADD2/FFMA2.
 // Tiles are the leaves of a kd-tree over the training points (built on the host at fit time), so a
 // tile is spatially compact and its box test can prove that every pair term flushes to zero.
-constexpr int TN = 256;              // training points per tile
-#ifndef SKB_NSTAGE
-#define SKB_NSTAGE 4
+#ifndef SKB_TN
+#define SKB_TN 128
 #endif
-constexpr int NSTAGE = SKB_NSTAGE;   // TMA ring depth
+constexpr int TN = SKB_TN;           // training points per tile (kd leaf size)
+#ifndef SKB_NSTAGE
+#define SKB_NSTAGE 3
+#endif
+#ifndef SKB_NSTAGE_HI
+#define SKB_NSTAGE_HI 2
+#endif
+// TMA ring depth (shared memory per CTA = depth x tile bytes; D > 8 tiles are twice as large)
+__host__ __device__ constexpr int nstage(int D) { return D <= 8 ? SKB_NSTAGE : SKB_NSTAGE_HI; }
 #ifndef SKB_NT
-#define SKB_NT 128
+#define SKB_NT 32
 #endif
 constexpr int NT = SKB_NT;           // threads per CTA of the score kernel
 constexpr int FB = 32;               // queries per finalize block (arrival-counter granularity)
@@ -30,13 +37,13 @@ constexpr int SG = 16;               // tiles per super-box (consecutive kd leav
 constexpr float PAD_COORD = 1.0e18f; // coordinate of padding / zero-weight points: exp2(-1e36) == 0
 
 #ifndef SKB_Q_LE2
-#define SKB_Q_LE2 8
+#define SKB_Q_LE2 2
 #endif
 #ifndef SKB_Q_LE4
-#define SKB_Q_LE4 8
+#define SKB_Q_LE4 2
 #endif
 #ifndef SKB_Q_LE8
-#define SKB_Q_LE8 4
+#define SKB_Q_LE8 2
 #endif
 #ifndef SKB_Q_LE16
 #define SKB_Q_LE16 2
@@ -46,7 +53,7 @@ constexpr float PAD_COORD = 1.0e18f; // coordinate of padding / zero-weight poin
 #ifndef SKB_MB_HI
 #define SKB_MB_HI 4
 #endif
-__host__ __device__ constexpr int min_blocks_per_sm(int D) { return D <= 3 ? 4 : (D == 4 ? 2 : (D <= 8 ? 3 : SKB_MB_HI)); }
+__host__ __device__ constexpr int min_blocks_per_sm(int D) { return D <= 8 ? 4 : SKB_MB_HI; }   // x (128 / NT) CTAs
 __host__ __device__ constexpr int queries_per_thread(int D)
 {
     return D <= 2 ? SKB_Q_LE2 : (D <= 4 ? SKB_Q_LE4 : (D <= 8 ? SKB_Q_LE8 : SKB_Q_LE16));
@@ -54,7 +61,7 @@ __host__ __device__ constexpr int queries_per_thread(int D)
 // small-batch variant: fewer queries per thread -> more CTAs when the query table is short.  A query's
 // arithmetic does not depend on Q (each query is a private register chain), so both variants give
 // bit-identical results and the planner may pick either.
-__host__ __device__ constexpr int queries_per_thread_small(int D) { return D <= 8 ? 2 : 1; }
+__host__ __device__ constexpr int queries_per_thread_small(int D) { return 1; }
 __host__ __device__ constexpr int stage_floats(int D) { return (D + 2) * TN; }   // D coords, weights, header (box)
 
 // Device-resident description of one fitted KDE (one per handle, uploaded at skb_create).

@@ -316,6 +316,7 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
     constexpr int STAGE_FLOATS = stage_floats(D);
     constexpr uint32_t STAGE_BYTES = STAGE_FLOATS * sizeof(float);
     constexpr int NWARP = NT / 32;
+    constexpr int NSTAGE = nstage(D);
 
     const ScoreJob& job = L.jobs[blockIdx.y];
     const long long M = job.M;
@@ -758,6 +759,7 @@ template <int D, int Q>
 static cudaError_t launch_score_dq(const ScoreLaunch& L, int njobs, long long max_qblocks, int max_split,
                                    int max_ntiles, cudaStream_t st)
 {
+    constexpr int NSTAGE = nstage(D);
     const size_t smem = (size_t)NSTAGE * stage_floats(D) * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t) +
                         (((size_t)max_ntiles + 31) / 32) * 4 + 16;
     cudaError_t e = cudaFuncSetAttribute(skb_score_kernel<D, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -781,7 +783,8 @@ cudaError_t read_stats(unsigned long long* out4, int reset)
 template <int D, int Q>
 static int occupancy_dq()
 {
-    const size_t smem = (size_t)NSTAGE * stage_floats(D) * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t);
+    constexpr int NSTAGE = nstage(D);
+    const size_t smem = (size_t)NSTAGE * stage_floats(D) * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t) + 1024;
     int n = 0;
     if (cudaFuncSetAttribute(skb_score_kernel<D, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, skb_score_kernel<D, Q>, NT, smem) != cudaSuccess) {
