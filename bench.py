@@ -389,15 +389,14 @@ def run_ours(args):
             except Exception:
                 traffic = None
         flop_pair = 3 * D + 1
-        # executed pairs: 64-point blocks actually evaluated (warp level) x 64 points x 32 lanes x Q queries
-        q_per_thread = 4
-        exec_pairs_per_launch = st[1] * 64.0 * 32.0 * q_per_thread / max(args.steps, 1)
+        # executed pairs: (64-point blocks x queries per thread, warp level) x 64 points x 32 lanes
+        exec_pairs_per_launch = st[1] * 64.0 * 32.0 / max(args.steps, 1)
         exec_frac = exec_pairs_per_launch / pairs_per_step_rank
         ach_exec = exec_pairs_per_launch / (kernel_ms * 1e-3)
         dense_rate = pairs_per_step_rank / (dense_ms * 1e-3)
         roof = {
             # bound: the FP32 FMA pipe (with the SFU as second limit) — not HBM, not tensor cores
-            "bound": "fp32", "kernel": "skb::skb_score_kernel<8,4>",
+            "bound": "fp32", "kernel": "skb::skb_score_kernel<8,2>",
             "achieved": ach * flop_pair / 1e12, "peak": peak_pairs * flop_pair / 1e12, "unit": "TFLOP/s",
             "frac": ach / peak_pairs, "traffic": traffic,
             "definition": "achieved = ALGORITHMIC work: pairs/launch x (3d+1) FP32 FLOP / CUDA-event launch time, "

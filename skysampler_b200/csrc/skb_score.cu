@@ -81,8 +81,9 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// diagnostics (warp level): [0] overflow re-runs of a 64-point block, [1] 64-point blocks processed,
-// [2] tiles culled by the box test, [3] tiles visited
+// diagnostics (warp level): [0] overflow re-runs of a 64-point block x queries per thread, [1] 64-point
+// blocks processed x queries per thread (x 64 x 32 = pairs evaluated), [2] tiles culled by the box tests,
+// [3] tiles in range
 __device__ unsigned long long g_stats[4];
 
 constexpr float OVERFLOW_LIMIT = 1.329228e36f;    // 2^120: a block partial sum at/above this is re-run
@@ -279,6 +280,13 @@ __device__ __forceinline__ void merge_partials(const double2* __restrict__ parti
 
 constexpr double LN2 = 0.693147180559945309417232121458;
 
+// one rounding sequence for every path that turns (m, S) into log p (no FMA contraction), so the register
+// epilogue and the partial-state epilogue give the same bits
+__device__ __forceinline__ double final_logp(double log_norm, double S, double m)
+{
+    return __dadd_rn(__dadd_rn(log_norm, log(S)), -__dmul_rn(m, LN2));
+}
+
 __device__ __forceinline__ void finalize_query(const FinTable& fin, int first, int count,
                                                long long M, long long v)
 {
@@ -291,7 +299,7 @@ __device__ __forceinline__ void finalize_query(const FinTable& fin, int first, i
         double mstar, S;
         merge_partials(fj.partial, fj.nsplit, M, v, mstar, S);
         if (fj.out_m) { fj.out_m[r] = fj.log_wmax - mstar * LN2; fj.out_s[r] = S; }
-        const double lp = fj.log_norm + log(S) - mstar * LN2;
+        const double lp = final_logp(fj.log_norm, S, mstar);
         if (fj.out_logp) fj.out_logp[r] = lp;
         log_ratio += fj.sign * lp + fj.sign_logjac;
     }
@@ -703,8 +711,8 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
     }
 
     if (lane == 0) {
-        if (n_rerun) atomicAdd(&g_stats[0], (unsigned long long)n_rerun);
-        atomicAdd(&g_stats[1], (unsigned long long)n_blocks);
+        if (n_rerun) atomicAdd(&g_stats[0], (unsigned long long)n_rerun * Q);
+        atomicAdd(&g_stats[1], (unsigned long long)n_blocks * Q);
         atomicAdd(&g_stats[2], (unsigned long long)(n_culled + (unsigned)ntl - n_visited));
         atomicAdd(&g_stats[3], (unsigned long long)ntl);      // tiles of the split (culled = box-culled at either level)
     }
@@ -719,7 +727,7 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
             if (v < M) {
                 const long long r = job.perm ? job.perm[v] : v;          // row of the query table
                 if (myfin.out_m) { myfin.out_m[r] = myfin.log_wmax - (double)mref[q] * LN2; myfin.out_s[r] = S[q]; }
-                if (myfin.out_logp) myfin.out_logp[r] = myfin.log_norm + log(S[q]) - (double)mref[q] * LN2;
+                if (myfin.out_logp) myfin.out_logp[r] = final_logp(myfin.log_norm, S[q], (double)mref[q]);
             }
         }
         return;

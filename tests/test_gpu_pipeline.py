@@ -187,3 +187,17 @@ def test_kfold_cv_bandwidth_scores():
     lp = brute64.score(zz[tr], ww[tr], 0.3, zz[te][first])
     ref = np.sum(ww[te][first] * (lp + np.log(abs(cvb.cont._jacobian_det)))) / np.sum(ww[te][first])
     assert abs(rb[0] - ref) <= 1e-4 * max(1.0, abs(ref))
+
+
+def test_group_and_single_paths_give_the_same_bits():
+    """score_samples (register epilogue) and the fused group path (partial state + last-arriver
+    epilogue) must agree bit for bit — smoke() relies on it."""
+    from skysampler_b200 import KDEContainer, emulator, synth
+    df, w = synth.frame(4, 10000, 101)
+    c = KDEContainer(df, w, seed=1)
+    c.standardize_data(); c.construct_kde(0.1)
+    prop = c.random_draw(20000)
+    lp, _ = c.score_samples(prop)
+    out = emulator.score_group([c], [list(df.columns)], prop, sign=[1], log_m=0.0, u=np.random.RandomState(1).uniform(size=len(prop)))
+    assert np.array_equal(out["logp"][0], lp)
+    c.drop_kde()
