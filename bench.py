@@ -234,7 +234,11 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("SKB_NCCL_DEBUG", "WARN")    # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: NCCL prints its version banner there at any NCCL_DEBUG level
+        if "SKB_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["SKB_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=dev)
     lib = _cabi.lib()
 

@@ -11,7 +11,7 @@ from oracle import brute64
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
-os.environ["NCCL_DEBUG"] = "WARN"
+os.environ.pop("NCCL_DEBUG", None)
 dist.init_process_group("nccl", device_id=dev)
 d, n, m, h = 8, 300000, 200000, 0.1
 if rank == 0:
