@@ -52,6 +52,9 @@ def _as_matrix(x, allow_torch=True):
         raise ValueError("Expected 2D array, got %dD array instead" % x.ndim)
     if x.dtype != np.float32:
         x = x.astype(np.float64, copy=False)
+    if not np.isfinite(x).all():
+        # sklearn's validate_data raises the same way (KernelDensity.fit / score_samples, _kde.py:233,272)
+        raise ValueError("Input X contains NaN or infinity.")
     return np.ascontiguousarray(x)
 
 

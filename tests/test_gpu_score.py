@@ -107,6 +107,10 @@ def test_empty_query_and_dimension_mismatch():
         _kde(rs.normal(size=(10, 2)), -np.ones(10), 0.2)
     with pytest.raises(ValueError):
         _kde(rs.normal(size=(10, 2)), np.ones(9), 0.2)
+    with pytest.raises(ValueError):                       # sklearn validate_data rejects NaN / inf the same way
+        kde.score_samples(np.array([[0.0, np.nan, 0.0]]))
+    with pytest.raises(ValueError):
+        _kde(np.array([[0.0, np.inf], [1.0, 2.0]]), None, 0.2)
     kde.close()
     with pytest.raises(RuntimeError):
         kde.score_samples(np.zeros((5, 3)))
