@@ -21,6 +21,12 @@
  *   - no torch types, no C++ types; plain pointers and sizes only.
  *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
  *     SKB_ECUDA.
+ *   - every (query, training) pair is accounted for exactly as the all-pairs sum in fp32 terms /
+ *     fp64 log-sum-exp would: tiles of training points whose bounding box proves that all their terms
+ *     flush to zero are skipped (kd-ordered tiles, Morton-ordered queries).  SKB_NO_CULL=1 in the
+ *     environment evaluates every pair (diagnostics).  A query's result never depends on the other rows
+ *     of the call: any batching / sharding of the query table is bit-identical.
+ *   - one call at a time per handle: scratch buffers are owned by the handle.
  */
 #ifndef SKB_H
 #define SKB_H
