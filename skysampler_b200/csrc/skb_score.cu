@@ -2,24 +2,27 @@
 // `kernel_density` walk (sklearn neighbors/_binary_tree.pxi.tp:1393-1535, 2149-2290) that
 // skysampler's KDEContainer.score_samples reaches (skysampler/emulator.py:380-385).
 //
-// Every (query, training point) pair is evaluated — no tree, no tolerance:
+// Every (query, training point) pair is accounted for — no tolerance:
 //     log p(z) = log_norm + log sum_j w_j exp(-|z - z_j|^2 / 2h^2)
 // with fp32 pair terms and an fp64 log-sum-exp state per query.
 //
-// Per pair the FMA pipe sees exactly 2D+1 lane operations (D subtractions, D fused squares, one
-// weighted accumulate) and the SFU one EX2:
+// Arithmetic.  Per evaluated pair the FMA pipe sees exactly 2D+1 lane operations (D subtractions, D fused
+// squares, one weighted accumulate) and the SFU one EX2:
 //   * coordinates are prescaled by c = sqrt(log2(e)/2)/h so that exp(-d^2/2h^2) = exp2(-|c dz|^2);
-//   * the per-query reference exponent m is folded into the accumulator seed (acc starts at -m),
-//     so no per-pair shift is needed; m only has to lie in a ~216-binade window around the true
-//     minimum distance.  It is seeded by a min-only pass over the first tile of a split and
-//     corrected lazily: a 64-point block whose fp32 partial sum overflows is re-run after a
+//   * the per-query reference exponent m is folded into the accumulator seed (acc starts at -m), so no
+//     per-pair shift is needed; m only has to lie in a ~216-binade window around the true minimum
+//     distance.  It comes from an exact evaluation of the query's home tile and is tightened from the
+//     exponents of the block sums; a 64-point block whose fp32 partial sum overflows is re-run after a
 //     min-only pass over that block (rare);
 //   * the weight is applied as sum = fma(w_j, e, sum) — same cost as an add;
-//   * two training points ride in one FADD2/FFMA2 (packed fp32x2, one issue slot for two lane
-//     ops), which leaves issue slots for MUFU.EX2 and LDS — measured on B200: 8xFFMA2 + 2xMUFU
-//     per loop co-issue at 98% of the FMA peak, the scalar form is issue-bound at 80%.
-// Training tiles arrive in shared memory through a 4-deep ring of 1-D TMA bulk copies
-// (cp.async.bulk + mbarrier complete_tx); all lanes of a warp read the same tile words
+//   * two training points ride in one FADD2/FFMA2 (packed fp32x2, one issue slot for two lane ops), which
+//     leaves issue slots for MUFU.EX2 and LDS — measured on B200: 8xFFMA2 + 2xMUFU per loop co-issue at
+//     98% of the FMA peak, the scalar form is issue-bound at 80%.
+// Culling.  Training tiles are kd-tree leaves with bounding boxes and a warp's queries are Morton
+// neighbours: a tile whose box is > 128 binades beyond every reference of the warp has only terms that
+// flush to zero in the arithmetic above and is skipped (never even loaded when the whole CTA agrees).
+// Data movement.  One warp per CTA; its needed tiles arrive in shared memory through a private ring of
+// 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx); all lanes read the same tile words
 // (LDS.128 broadcast), each thread owning Q whole queries, so no cross-lane reduction exists.
 #include "skb_internal.h"
 #include <math.h>
