@@ -261,7 +261,7 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
         if (done[j0]) continue;
         const int D = jobs[j0].h->hk.D;
         int nl = 0;
-        long long max_rows = 0, total_rows_splits = 0;
+        long long max_rows = 0;
         int max_split = 1, max_ntiles = 0;
         for (int j = j0; j < n; j++) {
             if (done[j] || jobs[j].h->hk.D != D) continue;
@@ -302,17 +302,15 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
                 }
             }
             if (dj.M > max_rows) max_rows = dj.M;
-            total_rows_splits += ((dj.M + NT * queries_per_thread(D) - 1) / (NT * queries_per_thread(D))) * nsplit[j];
             if (nsplit[j] > max_split) max_split = nsplit[j];
             if (dj.h->hk.ntiles > max_ntiles) max_ntiles = dj.h->hk.ntiles;
         }
-        // short query tables: fewer queries per thread -> more CTAs (same bits, see skb_internal.h)
-        bool small_q = total_rows_splits < 2LL * jobs[j0].h->sms * score_ctas_per_sm(D, false);
-        if (const char* fq = getenv("SKB_FORCE_SMALLQ")) small_q = atoi(fq) != 0;      // experiments only
-        const int QB = NT * (small_q ? queries_per_thread_small(D) : queries_per_thread(D));
+        // culling off -> the instantiation tuned for all-pairs evaluation (same bits, see skb_internal.h)
+        const bool dense_q = !cull;
+        const int QB = NT * (dense_q ? queries_per_thread_dense(D) : queries_per_thread(D));
         const long long max_qblocks = (max_rows + QB - 1) / QB;
         if (max_qblocks > 0x7fffffffLL) return fail(SKB_EINVAL, "too many query rows for one launch");
-        if (max_qblocks > 0) SKB_CUDA(launch_score(D, small_q, L, nl, max_qblocks, max_split, max_ntiles, st));
+        if (max_qblocks > 0) SKB_CUDA(launch_score(D, dense_q, L, nl, max_qblocks, max_split, max_ntiles, st));
     }
     return SKB_OK;
 }

@@ -43,10 +43,10 @@ constexpr float PAD_COORD = 1.0e18f; // coordinate of padding / zero-weight poin
 #define SKB_Q_LE4 2
 #endif
 #ifndef SKB_Q_LE8
-#define SKB_Q_LE8 2
+#define SKB_Q_LE8 1
 #endif
 #ifndef SKB_Q_LE16
-#define SKB_Q_LE16 2
+#define SKB_Q_LE16 1
 #endif
 // resident CTAs per SM the register allocator is asked to allow (measured on B200, tools/perf_scan.py:
 // d<=3 and d>=9 like 4 CTAs/SM with 128 registers, d=4 likes 2 CTAs with 232, d=5..8 like 3 with 168)
@@ -58,10 +58,10 @@ __host__ __device__ constexpr int queries_per_thread(int D)
 {
     return D <= 2 ? SKB_Q_LE2 : (D <= 4 ? SKB_Q_LE4 : (D <= 8 ? SKB_Q_LE8 : SKB_Q_LE16));
 }
-// small-batch variant: fewer queries per thread -> more CTAs when the query table is short.  A query's
-// arithmetic does not depend on Q (each query is a private register chain), so both variants give
-// bit-identical results and the planner may pick either.
-__host__ __device__ constexpr int queries_per_thread_small(int D) { return 1; }
+// Second instantiation, tuned for the all-pairs evaluation (culling off, SKB_NO_CULL=1): more queries per
+// thread = more independent FMA chains and fewer LDS per pair.  A query's arithmetic does not depend on Q
+// (each query is a private register chain), so both variants give bit-identical results.
+__host__ __device__ constexpr int queries_per_thread_dense(int D) { return D <= 4 ? 8 : (D <= 8 ? 4 : 2); }
 __host__ __device__ constexpr int stage_floats(int D) { return (D + 2) * TN; }   // D coords, weights, header (box)
 
 // Device-resident description of one fitted KDE (one per handle, uploaded at skb_create).
@@ -146,9 +146,9 @@ cudaError_t launch_query_order(const KdeDev* kde, const void* q, int q_f32, long
                                int q_is_whitened, const signed char* cols_dev, unsigned long long* keys_in,
                                unsigned long long* keys_out, int* idx_in, int* idx_out, void* temp, size_t temp_bytes,
                                cudaStream_t st);
-cudaError_t launch_score(int D, bool small_q, const ScoreLaunch& L, int njobs, long long max_qblocks, int max_split,
+cudaError_t launch_score(int D, bool dense_q, const ScoreLaunch& L, int njobs, long long max_qblocks, int max_split,
                          int max_ntiles, cudaStream_t st);
-int score_ctas_per_sm(int D, bool small_q);
+int score_ctas_per_sm(int D, bool dense_q);
 cudaError_t launch_draw(const KdeDev* kde, int D, long long M, const double* u, const double* z,
                         uint64_t seed, uint64_t offset, const long long* rows,
                         int rcol, double rmin, double rmax, int max_attempts,

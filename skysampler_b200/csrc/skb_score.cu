@@ -320,7 +320,7 @@ __device__ __forceinline__ void finalize_query(const FinTable& fin, int first, i
 // The score kernel.  grid = (query blocks, jobs, training splits), block = NT threads.
 // ---------------------------------------------------------------------------------------------
 template <int D, int Q>
-__global__ void __launch_bounds__(NT, (Q == queries_per_thread(D) ? min_blocks_per_sm(D) : 4) * (128 / NT))
+__global__ void __launch_bounds__(NT, (Q == queries_per_thread(D) ? min_blocks_per_sm(D) : (D <= 4 ? 2 : (D <= 8 ? 3 : 4))) * (128 / NT))
 skb_score_kernel(const __grid_constant__ ScoreLaunch L)
 {
     constexpr int QB = NT * Q;
@@ -805,14 +805,14 @@ static int occupancy_dq()
     return n > 0 ? n : 1;
 }
 
-int score_ctas_per_sm(int D, bool small_q)
+int score_ctas_per_sm(int D, bool dense_q)
 {
     static int cache[2][SKB_MAXD + 1] = {{0}, {0}};
     if (D < 1 || D > SKB_MAXD) return 1;
-    int& c = cache[small_q ? 1 : 0][D];
+    int& c = cache[dense_q ? 1 : 0][D];
     if (c == 0) {
         switch (D) {
-#define SKB_CASE(d) case d: c = small_q ? occupancy_dq<d, queries_per_thread_small(d)>() \
+#define SKB_CASE(d) case d: c = dense_q ? occupancy_dq<d, queries_per_thread_dense(d)>() \
                                         : occupancy_dq<d, queries_per_thread(d)>(); break;
             SKB_CASE(1) SKB_CASE(2) SKB_CASE(3) SKB_CASE(4) SKB_CASE(5) SKB_CASE(6) SKB_CASE(7) SKB_CASE(8)
             SKB_CASE(9) SKB_CASE(10) SKB_CASE(11) SKB_CASE(12) SKB_CASE(13) SKB_CASE(14) SKB_CASE(15) SKB_CASE(16)
@@ -824,11 +824,11 @@ int score_ctas_per_sm(int D, bool small_q)
 
 static_assert(sizeof(ScoreLaunch) <= 4000, "ScoreLaunch must fit the classic 4 KB kernel-parameter space");
 
-cudaError_t launch_score(int D, bool small_q, const ScoreLaunch& L, int njobs, long long max_qblocks, int max_split,
+cudaError_t launch_score(int D, bool dense_q, const ScoreLaunch& L, int njobs, long long max_qblocks, int max_split,
                          int max_ntiles, cudaStream_t st)
 {
     switch (D) {
-#define SKB_CASE(d) case d: return small_q ? launch_score_dq<d, queries_per_thread_small(d)>(L, njobs, max_qblocks, max_split, max_ntiles, st) \
+#define SKB_CASE(d) case d: return dense_q ? launch_score_dq<d, queries_per_thread_dense(d)>(L, njobs, max_qblocks, max_split, max_ntiles, st) \
                                            : launch_score_dq<d, queries_per_thread(d)>(L, njobs, max_qblocks, max_split, max_ntiles, st);
         SKB_CASE(1) SKB_CASE(2) SKB_CASE(3) SKB_CASE(4) SKB_CASE(5) SKB_CASE(6) SKB_CASE(7) SKB_CASE(8)
         SKB_CASE(9) SKB_CASE(10) SKB_CASE(11) SKB_CASE(12) SKB_CASE(13) SKB_CASE(14) SKB_CASE(15) SKB_CASE(16)
