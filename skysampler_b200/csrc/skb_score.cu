@@ -102,6 +102,9 @@ constexpr float CULL_MARGIN = 128.f;              // box lower bound this far pa
 #ifndef SKB_POLY_EXP
 #define SKB_POLY_EXP 1     // 1: for D == 1 a quarter of the exponentials run as a polynomial on the FMA pipe
 #endif
+#ifndef SKB_STEP8
+#define SKB_STEP8 1       // 1: 8 training points per inner step when a thread holds <= 2 queries
+#endif
 #ifndef SKB_PREFETCH
 #define SKB_PREFETCH 0     // 1: double-buffer the tile words of the next 4 points in registers
 #endif
@@ -217,6 +220,56 @@ __device__ __forceinline__ void step_compute(const StepOperands<D>& op, const u6
     }
 }
 
+// 8 points per step (four packed pairs per dimension): with Q <= 2 queries per thread a 4-point step has
+// only 2Q independent FMA chains in flight, too few to cover the FFMA2 latency; this doubles them.
+template <int D, int Q, bool MIN_ONLY>
+__device__ __forceinline__ void step_compute8(const float* __restrict__ tile, int j, const u64 (&q2)[Q][D],
+                                              const u64 (&nm2)[Q], u64 (&sum2)[Q], float (&amin)[Q])
+{
+    u64 xa[D], xb[D], xc[D], xd[D];
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        const float4 v = *reinterpret_cast<const float4*>(tile + k * TN + j);
+        const float4 u = *reinterpret_cast<const float4*>(tile + k * TN + j + 4);
+        xa[k] = pk(v.x, v.y); xb[k] = pk(v.z, v.w); xc[k] = pk(u.x, u.y); xd[k] = pk(u.z, u.w);
+    }
+    u64 wa = 0, wb = 0, wc = 0, wd = 0;
+    if (!MIN_ONLY) {
+        const float4 w4 = *reinterpret_cast<const float4*>(tile + D * TN + j);
+        const float4 w5 = *reinterpret_cast<const float4*>(tile + D * TN + j + 4);
+        wa = pk(w4.x, w4.y); wb = pk(w4.z, w4.w); wc = pk(w5.x, w5.y); wd = pk(w5.z, w5.w);
+    }
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        u64 aa = nm2[q], ab = nm2[q], ac = nm2[q], ad = nm2[q];
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            const u64 da = sub2(q2[q][k], xa[k]);
+            const u64 db = sub2(q2[q][k], xb[k]);
+            const u64 dc = sub2(q2[q][k], xc[k]);
+            const u64 dd = sub2(q2[q][k], xd[k]);
+            aa = fma2(da, da, aa);
+            ab = fma2(db, db, ab);
+            ac = fma2(dc, dc, ac);
+            ad = fma2(dd, dd, ad);
+        }
+        float a0, a1, b0, b1, c0, c1, d0, d1;
+        upk(aa, a0, a1); upk(ab, b0, b1); upk(ac, c0, c1); upk(ad, d0, d1);
+        if (MIN_ONLY) {
+            amin[q] = min3(amin[q], a0, a1);
+            amin[q] = min3(amin[q], b0, b1);
+            amin[q] = min3(amin[q], c0, c1);
+            amin[q] = min3(amin[q], d0, d1);
+        } else {
+            // same accumulation order as two 4-point steps: (a, b) then (c, d)
+            sum2[q] = fma2(wa, pk(ex2_neg(a0), ex2_neg(a1)), sum2[q]);
+            sum2[q] = fma2(wb, pk(ex2_neg(b0), ex2_neg(b1)), sum2[q]);
+            sum2[q] = fma2(wc, pk(ex2_neg(c0), ex2_neg(c1)), sum2[q]);
+            sum2[q] = fma2(wd, pk(ex2_neg(d0), ex2_neg(d1)), sum2[q]);
+        }
+    }
+}
+
 // npts must be a multiple of 8.
 template <int D, int Q, bool MIN_ONLY>
 __device__ __forceinline__ void tile_pass(const float* __restrict__ tile, int npts,
@@ -247,6 +300,9 @@ __device__ __forceinline__ void tile_pass(const float* __restrict__ tile, int np
             A.template load<!MIN_ONLY>(tile, j + 4);
             step_compute<D, Q, MIN_ONLY, kPoly>(A, q2, nm2, sum2, amin);
         }
+    } else if (SKB_STEP8 && Q * D <= 16) {
+#pragma unroll 1
+        for (int j = 0; j < npts; j += 8) step_compute8<D, Q, MIN_ONLY>(tile, j, q2, nm2, sum2, amin);
     } else {
 #pragma unroll 1
         for (int j = 0; j < npts; j += 4) {
