@@ -367,3 +367,22 @@ def test_culling_with_disjoint_clusters_and_outliers():
     assert np.abs(got - ref)[near].max() <= 1e-4
     assert (np.abs(got - ref) / np.maximum(1.0, np.abs(ref))).max() <= 1e-5
     kde.close()
+
+
+def test_degenerate_geometry():
+    """Zero-size boxes, identical points, identical queries, one training point, heavy duplicates."""
+    rs = np.random.RandomState(41)
+    # all training points identical
+    z = np.tile(np.array([[0.3, -0.2, 1.1]]), (700, 1)); q = rs.normal(size=(300, 3))
+    kde = _kde(z, rs.uniform(0.1, 1, 700), 0.3)
+    _check(kde.score_samples(q), brute64.score(z, None, 0.3, q)); kde.close()
+    # a single training point, thousands of identical queries
+    z1 = np.array([[1.0, 2.0]]); q1 = np.tile(np.array([[1.5, 1.0]]), (5000, 1))
+    kde = _kde(z1, None, 0.5)
+    got = kde.score_samples(q1); ref = brute64.score(z1, None, 0.5, q1)
+    assert np.abs(got - ref).max() <= 1e-5 and np.unique(got).size == 1; kde.close()
+    # a lattice with many exact duplicates and one constant coordinate
+    g = np.stack(np.meshgrid(np.arange(8.0), np.arange(8.0), [0.0]), -1).reshape(-1, 3)
+    z = np.repeat(g, 40, axis=0); q = np.vstack([g + 0.01, 4.0 + 3.0 * rs.normal(size=(2000, 3))])
+    kde = _kde(z, None, 0.2)
+    _check(kde.score_samples(q), brute64.score(z, None, 0.2, q)); kde.close()
