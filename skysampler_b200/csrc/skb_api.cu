@@ -349,7 +349,7 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
     if (train_dtype != SKB_F64 && train_dtype != SKB_F32) return fail(SKB_EINVAL, "bad train dtype %d", train_dtype);
     if ((mu == nullptr) != (W == nullptr)) return fail(SKB_EINVAL, "mu and W must be given together");
     if (!train_is_whitened && !W) return fail(SKB_EINVAL, "raw training rows need the whitening map (mu, W)");
-    if (N > (1LL << 40)) return fail(SKB_EINVAL, "training set too large");
+    if (N >= (1LL << 31)) return fail(SKB_EINVAL, "training set too large (row ids are 32-bit): shard it over GPUs");
     int ndev = skb_device_count();
     if (ndev <= 0) return fail(SKB_ECUDA, "no CUDA device available (this backend has no CPU fallback)");
     if (device < 0 || device >= ndev) return fail(SKB_EINVAL, "device %d out of range (0..%d)", device, ndev - 1);

@@ -33,7 +33,10 @@ __host__ __device__ constexpr int nstage(int D) { return D <= 8 ? SKB_NSTAGE : S
 #endif
 constexpr int NT = SKB_NT;           // threads per CTA of the score kernel
 constexpr int FB = 32;               // queries per finalize block (arrival-counter granularity)
-constexpr int SG = 16;               // tiles per super-box (consecutive kd leaves = one kd subtree)
+#ifndef SKB_SG
+#define SKB_SG 16
+#endif
+constexpr int SG = SKB_SG;               // tiles per super-box (consecutive kd leaves = one kd subtree)
 constexpr float PAD_COORD = 1.0e18f; // coordinate of padding / zero-weight points: exp2(-1e36) == 0
 
 #ifndef SKB_Q_LE2
