@@ -386,3 +386,19 @@ def test_degenerate_geometry():
     z = np.repeat(g, 40, axis=0); q = np.vstack([g + 0.01, 4.0 + 3.0 * rs.normal(size=(2000, 3))])
     kde = _kde(z, None, 0.2)
     _check(kde.score_samples(q), brute64.score(z, None, 0.2, q)); kde.close()
+
+
+def test_handles_release_device_memory():
+    """construct / score / drop in a loop (what calc_scores does per chunk) must not leak device memory."""
+    import torch
+    rs = np.random.RandomState(51)
+    z = rs.normal(size=(50000, 4)); q = rs.normal(size=(20000, 4))
+    for _ in range(3):
+        k = _kde(z, None, 0.1); k.score_samples(q); k.close()
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(60):
+        k = _kde(z, rs.uniform(0.5, 1, 50000), 0.1); k.score_samples(q); k.sample_philox(1000, seed=1); k.close()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 64 * 2 ** 20, (free0, free1)
