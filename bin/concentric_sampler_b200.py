@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Concentric-shell sampler on synthetic containers (BASELINE.json config 3): the loop of
 bin/epsilon_concentric_sampler_v05.py:127-181 with every shell fitted up front and all shell KDEs
-scored as one batched launch.  Prints a JSON summary; writes <out>_rbin{i}_{samples,scores}.npz when
---out is given (the reference writes FITS through fitsio, which this image does not have).
+scored as one batched launch.  Prints a JSON summary; writes <out>_rbin{i}_samples.fits / _scores.fits when
+--out is given (through fitsio when installed, else skysampler_b200.fitsio_lite: same BINTABLE layout).
 
     python bin/concentric_sampler_b200.py --shells 10 --ntrain 100000 --nsamples 1000000
 """
@@ -59,9 +59,9 @@ def main():
                "kernel_launches": int(_cabi.lib().skb_launch_count() - l0),
                "note": "wall time includes host PCA fits, uploads, draws and pandas merges"}
     if args.out:
-        for i, (samples, scores) in enumerate(res):
-            np.savez_compressed("%s_rbin%d_samples.npz" % (args.out, i), **{c: samples[c].values for c in samples.columns})
-            np.savez_compressed("%s_rbin%d_scores.npz" % (args.out, i), **{c: scores[c].values for c in scores.columns})
+        from skysampler_b200 import emulator
+        for i, (samples, scores) in enumerate(res):          # the reference's per-shell files (v05 driver :162-181)
+            emulator.write_tables("%s_rbin%d" % (args.out, i), samples, scores)
     print(json.dumps(summary))
 
 

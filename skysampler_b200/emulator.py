@@ -322,3 +322,36 @@ def _score_cv_samples(info):
 def run_cv_scores(infodicts):
     """emulator.py:461-475, in-process."""
     return pd.concat([_score_cv_samples(info) for info in infodicts])
+
+
+# ------------------------------------------------------------------------------------------------
+# On-disk side of the accept step (emulator.py:717-748)
+# ------------------------------------------------------------------------------------------------
+def _fits():
+    try:
+        import fitsio as fio                      # the reference's reader / writer when it is installed
+        return fio
+    except Exception:
+        from . import fitsio_lite as fio          # same table layout, see the module header
+        return fio
+
+
+def read_concentric(score_path_expr, m_factor=20, seed=6):
+    """emulator.py:717-748: glob the ``*_scores.fits`` files, load the matching ``*_samples.fits``,
+    apply the accept test, return the accepted proposal rows (same DataFrame the reference returns)."""
+    import glob
+    fio = _fits()
+    fname_scores = np.sort(glob.glob(score_path_expr))
+    fname_samples = [f.replace("scores", "samples") for f in fname_scores]
+    samples = pd.concat([pd.DataFrame.from_records(fio.read(f)) for f in fname_samples])
+    scores = pd.concat([pd.DataFrame.from_records(fio.read(f)) for f in fname_scores])
+    inds = accept_concentric(scores, m_factor=m_factor, seed=seed)
+    return samples[inds]
+
+
+def write_tables(outname, samples, scores):
+    """The two per-shell files of the drivers: ``<outname>_samples.fits`` and ``<outname>_scores.fits``
+    (bin/epsilon_concentric_sampler_v05.py:162-164, 179-181), written from ``DataFrame.to_records()``."""
+    fio = _fits()
+    fio.write(outname + "_samples.fits", samples.to_records(), clobber=True)
+    fio.write(outname + "_scores.fits", scores.to_records(), clobber=True)

@@ -113,3 +113,35 @@ def test_synth_generators_are_seeded():
     m1, pm, comps, std2 = synth.whiten_params(a)
     z = (a - m1) @ comps.T / std2
     np.testing.assert_allclose(z.std(axis=0), 1.0, rtol=1e-10)
+
+
+def test_fits_tables_round_trip_and_read_concentric(tmp_path):
+    """_samples.fits / _scores.fits layout (one BINTABLE, big-endian scalar columns, 2880-byte blocks) and
+    the file-based accept step of read_concentric (emulator.py:717-748) against the golden masks."""
+    from skysampler_b200 import fitsio_lite
+    g = load_golden("driver_naive")
+    samples = pd.DataFrame(g["samples_exact"], columns=[str(c) for c in g["sample_columns"]])
+    scores = pd.DataFrame(g["scores_exact"], columns=[str(c) for c in g["score_columns"]])
+    out = str(tmp_path / "run_7_rbin0")
+    emulator.write_tables(out, samples, scores)
+    for suffix, df in (("_samples.fits", samples), ("_scores.fits", scores)):
+        raw = open(out + suffix, "rb").read()
+        assert len(raw) % 2880 == 0 and raw[:30].decode() == "SIMPLE  =                    T"
+        assert b"XTENSION= 'BINTABLE'" in raw[2880:5760]
+        rec = fitsio_lite.read(out + suffix)
+        assert rec.dtype.names[0] == "index" and list(rec.dtype.names[1:]) == list(df.columns)   # to_records() keeps the index
+        assert np.array_equal(rec["index"], np.arange(len(df)))
+        for c in df.columns:
+            assert np.array_equal(rec[c], df[c].values)                                            # bit exact
+    for m in (20, 2):
+        res = emulator.read_concentric(str(tmp_path / "run_*_scores.fits"), m_factor=m, seed=6)
+        assert np.array_equal(res[samples.columns].values, g["accepted_rows_m%d" % m])
+    with pytest.raises(IOError):
+        fitsio_lite.write(out + "_samples.fits", samples.to_records())                            # clobber=False
+    # mixed dtypes
+    rec = np.rec.fromarrays([np.arange(5, dtype=np.int64), np.arange(5, dtype=np.float32), np.arange(5, dtype=np.int32)],
+                            names="a,b,c")
+    fitsio_lite.write(str(tmp_path / "t.fits"), rec, clobber=True)
+    back = fitsio_lite.read(str(tmp_path / "t.fits"))
+    assert back.dtype["a"] == np.int64 and back.dtype["b"] == np.float32 and back.dtype["c"] == np.int32
+    assert np.array_equal(back["b"], rec["b"])
