@@ -43,6 +43,13 @@ def main():
     from skysampler_b200 import synth
     emu = load_reference()
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "features":
+        return features(emu)
+    kde_path(emu, synth)
+    features(emu)
+
+
+def kde_path(emu, synth):
 
     # ---------------------------------------------------------------- C1-shaped scoring vectors
     d, n = 4, 10000
@@ -157,6 +164,56 @@ def main():
         gold["accepted_rows_m%d" % m_factor] = resamples.values
         print("accept m=%d:" % m_factor, mask.sum(), "of", len(mask))
     np.savez_compressed(os.path.join(OUT, "driver_naive.npz"), **gold)
+
+
+def features(emu):
+    # ---------------------------------------------------------------- feature tables (emulator.py:67-231)
+    rs = np.random.RandomState(77)
+    nd = 3000
+    deep = np.zeros(nd, dtype=[("MAG_G", "f8"), ("MAG_R", "f8"), ("MAG_I", "f8"), ("MAG_Z", "f8"), ("SIZE", "f8"),
+                               ("E", "f8", (2,))])
+    for name, mu in (("MAG_G", 22.0), ("MAG_R", 21.5), ("MAG_I", 21.2), ("MAG_Z", 21.0)):
+        deep[name] = rs.normal(mu, 1, nd)
+    deep["SIZE"] = np.abs(rs.normal(0.5, 0.3, nd)) + 0.01
+    deep["E"] = rs.normal(size=(nd, 2))
+    deep_settings = {
+        "columns": [("MAG_I", "MAG_I"), ("COLOR_G_R", ("MAG_G", "MAG_R", "-")), ("COLOR_R_I", ("MAG_R", "MAG_I", "-")),
+                    ("LOGSIZE", "SIZE"), ("ELL", (("E", 0), ("E", 1), "SQSUM")), ("E1", ("E", 1))],
+        "logs": [False, False, False, True, False, False],
+        "limits": [(19, 24), (-1, 3), (-1, 3), (1e-3, 2.0), (0, 10), (-5, 5)],
+    }
+    dfc = emu.DeepFeatureContainer(deep)
+    dfc.construct_features(**deep_settings)
+    feat = dict(deep_MAG_G=deep["MAG_G"], deep_MAG_R=deep["MAG_R"], deep_MAG_I=deep["MAG_I"], deep_MAG_Z=deep["MAG_Z"],
+                deep_SIZE=deep["SIZE"], deep_E=deep["E"], deep_features=dfc.features.values,
+                deep_feature_index=np.asarray(dfc.features.index), deep_weights=np.asarray(dfc.weights))
+
+    class Info(object):
+        pass
+    info = Info()
+    nw = 6000
+    parts = []
+    for b in range(3):
+        parts.append(pd.DataFrame({"MAG_R": rs.normal(21, 1, nw // 3), "MAG_I": rs.normal(20.6, 1, nw // 3),
+                                   "DIST": 10 ** rs.uniform(-2.5, 1.0, nw // 3), "WEIGHT": rs.uniform(0.5, 2.0, nw // 3)}))
+    # (an EMPTY radial bin would take the reference through np.array(self.samples)[valid_elements],
+    #  emulator.py:156-158, which raises under numpy >= 1.24; the golden therefore has none)
+    info.samples = parts
+    info.redges = np.logspace(-2.5, 1.0, 8); info.rcens = np.sqrt(info.redges[1:] * info.redges[:-1])
+    info.rareas = np.pi * (info.redges[1:] ** 2 - info.redges[:-1] ** 2)
+    info.survey = None; info.numprof = None
+    info.target = Info(); info.target.nrow = 50
+    wide_settings = {"columns": [("COLOR_R_I", ("MAG_R", "MAG_I", "-")), ("LOGR", "DIST")], "logs": [False, True],
+                     "limits": [(-1, 3), (1e-3, 16.0)]}
+    fsc = emu.FeatureSpaceContainer(info)
+    fsc.construct_features(**wide_settings)
+    small = fsc.downsample(nmax=150, nbins=10, rng=np.random.RandomState(5))
+    feat.update(wide_parts=np.vstack([p.values.astype(float) for p in parts if len(p)]), wide_part_sizes=np.array([len(p) for p in parts]),
+                wide_redges=info.redges, wide_rareas=info.rareas, wide_features=fsc.features.values,
+                wide_weights=np.asarray(fsc.weights), wide_surfdens=fsc.surfdens(icol=1),
+                wide_down_data=small.data.values, wide_down_weights=np.asarray(small.weights))
+    np.savez_compressed(os.path.join(OUT, "features.npz"), **feat)
+    print("features: deep", dfc.features.shape, "wide", fsc.features.shape, "downsampled", small.data.shape)
 
 
 if __name__ == "__main__":

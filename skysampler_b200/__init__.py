@@ -5,6 +5,7 @@ Public surface (mirrors ``skysampler/emulator.py``):
     from skysampler_b200 import KDEContainer, GaussianKDE
     from skysampler_b200 import emulator      # make_*_infodicts, calc_scores*, run_scores*, accept_concentric, KFoldCV
     from skysampler_b200 import concentric    # batched concentric-shell driver;  pipeline: RatioSampler;  dist: multi-GPU
+    from skysampler_b200 import features      # construct_wide/deep_container, FeatureSpaceContainer, DeepFeatureContainer
 
 The compute lives in ``csrc/libskb.so`` (hand-written sm_100a CUDA behind the C ABI of
 ``include/skb.h``).  There is no CPU fallback.
