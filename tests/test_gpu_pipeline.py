@@ -201,3 +201,21 @@ def test_group_and_single_paths_give_the_same_bits():
     out = emulator.score_group([c], [list(df.columns)], prop, sign=[1], log_m=0.0, u=np.random.RandomState(1).uniform(size=len(prop)))
     assert np.array_equal(out["logp"][0], lp)
     c.drop_kde()
+
+
+def test_rejection_sampler_script_end_to_end(tmp_path):
+    """bin/rejection_sampler_b200.py: feature tables -> containers -> proposals -> scores -> FITS -> accept."""
+    import json, os, subprocess, sys
+    from conftest import ROOT
+    from skysampler_b200 import fitsio_lite
+    out = str(tmp_path / "delta")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bin", "rejection_sampler_b200.py"), "--ndeep", "20000", "--nwide", "40000",
+                        "--nsamples", "30000", "--nchunks", "4", "--out", out], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    assert info["proposals"] == 30000 and 0 < info["accepted"] < 30000
+    sc = fitsio_lite.read(out + "_scores.fits")
+    sm = fitsio_lite.read(out + "_samples.fits")
+    assert list(sc.dtype.names)[1:] == ["dc", "dc_jac", "wr", "wr_jac", "wcr", "wcr_jac"] and len(sm) == 30000
+    assert sm["LOGR"].max() <= np.log10(5.0) + 1e-12
+    assert np.all(np.isfinite(sc["wcr"])) and np.all(np.isfinite(sc["dc"])) and np.all(np.isfinite(sc["wr"]))
