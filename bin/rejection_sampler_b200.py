@@ -65,6 +65,9 @@ def main():
     ap.add_argument("--bandwidth", type=float, default=0.05)
     ap.add_argument("--out", default="/tmp/skysampler_b200_delta")
     ap.add_argument("--seed", type=int, default=5)
+    ap.add_argument("--rng", default="philox", choices=["philox", "host"],
+                    help="philox: device counter RNG, window redraws inside the kernel; host: consume numpy "
+                         "RandomState streams exactly as the reference does")
     args = ap.parse_args()
     from skysampler_b200 import emulator, features, _cabi
     deep, mdl = synthetic_inputs(args.ndeep, args.nwide, args.seed)
@@ -87,6 +90,8 @@ def main():
     deep_smc = features.construct_deep_container(deep, deep_smc_settings, seed=seeds[1])
     wide_cr = features.construct_wide_container(mdl, wide_cr_settings, seed=seeds[2])
     wide_r = features.construct_wide_container(mdl, wide_r_settings, seed=seeds[3])
+    for c in (deep_smc, wide_r):
+        c["container"]._rng_mode = args.rng
     t1 = time.time()
     infodicts, samples = emulator.make_naive_infodicts(wide_cr, wide_r, deep_c, deep_smc, columns, nsamples=args.nsamples,
                                                        nchunks=args.nchunks, bandwidth=args.bandwidth, rmin=None,
