@@ -86,3 +86,49 @@ class RatioSampler(object):
         flags_host.copy_(accept, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return flags_host, n, out[:n]
+
+    def run_host(self, batches):
+        """Pipelined end-to-end pass over a sequence of (rows, uniforms) batches in PINNED host memory:
+        the H2D copy of batch i+1 runs on a side stream while batch i is scored, accept flags and accepted
+        counts stream back asynchronously, one synchronisation at the end.  Returns (list of pinned uint8
+        flag tensors, list of accepted counts)."""
+        batches = list(batches)
+        if not batches:
+            return [], []
+        main = torch.cuda.current_stream(self.device)
+        side = getattr(self, "_side", None)
+        if side is None:
+            side = self._side = torch.cuda.Stream(device=self.device)
+        M, ld = batches[0][0].shape
+        slots = []
+        for s in range(2):
+            slots.append((self._get("q_pipe%d" % s, (M, ld), batches[0][0].dtype), self._get("u_pipe%d" % s, (M,), torch.float64),
+                          self._get("acc_pipe%d" % s, (M,), torch.uint8)))
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        free = [torch.cuda.Event(), torch.cuda.Event()]
+        flags_host = [torch.empty(M, dtype=torch.uint8, pin_memory=True) for _ in batches]
+        counts_host = torch.zeros(len(batches), dtype=torch.int64, pin_memory=True)
+
+        def upload(i):
+            qd, ud, _ = slots[i % 2]
+            with torch.cuda.stream(side):
+                if i >= 2:
+                    side.wait_event(free[i % 2])              # the kernels of batch i-2 are done with this slot
+                qd.copy_(batches[i][0], non_blocking=True)
+                ud.copy_(batches[i][1], non_blocking=True)
+                ready[i % 2].record(side)
+
+        upload(0)
+        for i in range(len(batches)):
+            if i + 1 < len(batches):
+                upload(i + 1)
+            qd, ud, keep = slots[i % 2]
+            main.wait_event(ready[i % 2])
+            accept, _, _, _ = self.score_accept(qd, ud, stream=main)
+            keep.copy_(accept)
+            self.compact(keep, qd, stream=main, sync_count=False)
+            free[i % 2].record(main)
+            flags_host[i].copy_(keep, non_blocking=True)
+            counts_host[i:i + 1].copy_(keep.sum(dtype=torch.int64).reshape(1), non_blocking=True)
+        main.synchronize()
+        return flags_host, [int(c) for c in counts_host]

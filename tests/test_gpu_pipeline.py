@@ -219,3 +219,31 @@ def test_rejection_sampler_script_end_to_end(tmp_path):
     assert list(sc.dtype.names)[1:] == ["dc", "dc_jac", "wr", "wr_jac", "wcr", "wcr_jac"] and len(sm) == 30000
     assert sm["LOGR"].max() <= np.log10(5.0) + 1e-12
     assert np.all(np.isfinite(sc["wcr"])) and np.all(np.isfinite(sc["dc"])) and np.all(np.isfinite(sc["wr"]))
+
+
+def test_pipelined_host_batches_equal_resident_steps():
+    """RatioSampler.run_host (H2D on a side stream, two slots) gives the flags and counts of step()."""
+    import torch
+    from skysampler_b200 import GaussianKDE
+    from skysampler_b200.pipeline import RatioSampler
+    rs = np.random.RandomState(61)
+    za = rs.normal(size=(30000, 4)); zb = 1.2 * rs.normal(size=(30000, 4))
+    ka = GaussianKDE(0.2).fit(za); kb = GaussianKDE(0.2).fit(zb)
+    s = RatioSampler([ka, kb], [1, -1], log_m=0.5, cols=None)
+    s.kdes[0]  # keep
+    M = 20000
+    qs = [torch.from_numpy(1.2 * rs.normal(size=(M, 4))).pin_memory() for _ in range(5)]
+    us = [torch.from_numpy(rs.uniform(size=M)).pin_memory() for _ in range(5)]
+    # handles were fitted on whitened rows without a map: score in whitened space through the group API needs W
+    ka.close(); kb.close()
+    I = np.eye(4)
+    ka = GaussianKDE(0.2).fit(za, whitening=(np.zeros(4), I, I)); kb = GaussianKDE(0.2).fit(zb, whitening=(np.zeros(4), I, I))
+    s = RatioSampler([ka, kb], [1, -1], log_m=0.5)
+    flags, counts = s.run_host(zip(qs, us))
+    for i in range(5):
+        acc, _, _, _ = s.score_accept(qs[i].cuda(), us[i].cuda())
+        assert np.array_equal(flags[i].numpy(), acc.cpu().numpy())
+        assert counts[i] == int(acc.sum().item())
+        rows, n = s.step(qs[i].cuda(), us[i].cuda())
+        assert n == counts[i] and np.array_equal(rows.cpu().numpy(), qs[i].numpy()[flags[i].numpy().astype(bool)])
+    ka.close(); kb.close()
