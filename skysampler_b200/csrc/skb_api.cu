@@ -106,6 +106,7 @@ struct DeviceGuard {
 // tiles (of super-boxes higher up) so that every tile except the last is a full leaf of TN points.
 static void kd_order(const float* z, int D, int* idx, long long n)
 {
+    const long long TN = tile_points(D);
     if (n <= TN) return;
     float lo[SKB_MAXD], hi[SKB_MAXD];
     for (int k = 0; k < D; k++) { lo[k] = INFINITY; hi[k] = -INFINITY; }
@@ -364,6 +365,7 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
     memset(&hk, 0, sizeof(hk));
     hk.N = N;
     hk.D = d;
+    const int TN = tile_points(d);
     hk.ntiles = (int)((N + TN - 1) / TN);
     hk.h = h;
     hk.c = std::sqrt(0.5 * 1.4426950408889634074) / h;   // sqrt(log2(e)/2)/h

@@ -40,6 +40,7 @@ __global__ void skb_whiten_kernel(const void* __restrict__ train, int f32, long 
 __global__ void skb_pack_kernel(const double* __restrict__ zt64, const int* __restrict__ perm, int D, double c,
                                 const double* __restrict__ w, double inv_wmax, float* __restrict__ tiles, int ntiles)
 {
+    const int TN = tile_points(D);
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= (long long)ntiles * TN) return;
     const long long t = s / TN;
@@ -60,6 +61,7 @@ __global__ void skb_pack_kernel(const double* __restrict__ zt64, const int* __re
 __global__ void skb_box_kernel(float* __restrict__ tiles, const int* __restrict__ perm, int D, int ntiles,
                                float* __restrict__ boxes)
 {
+    const int TN = tile_points(D);
     const int t = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
     const int lane = threadIdx.x & 31;
     if (t >= ntiles) return;
@@ -112,7 +114,7 @@ cudaError_t launch_fit(const void* train, int f32, long long N, int D, long long
 cudaError_t launch_pack(const double* zt64, const int* perm, int D, double c, const double* w, double inv_wmax,
                         float* tiles, int ntiles, float* boxes, float* sboxes, cudaStream_t st)
 {
-    const long long total = (long long)ntiles * TN;
+    const long long total = (long long)ntiles * tile_points(D);
     const int bs = 256;
     skb_pack_kernel<<<(unsigned)((total + bs - 1) / bs), bs, 0, st>>>(zt64, perm, D, c, w, inv_wmax, tiles, ntiles);
     skb_box_kernel<<<(unsigned)((ntiles + 7) / 8), 256, 0, st>>>(tiles, perm, D, ntiles, boxes);

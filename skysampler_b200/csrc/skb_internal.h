@@ -9,17 +9,22 @@ namespace skb {
 typedef unsigned long long u64;
 
 // ---- training-tile geometry -------------------------------------------------------------------
-// The fitted KDE lives in HBM as tiles of TN points in SoA order: tile t is one contiguous block
+// The fitted KDE lives in HBM as tiles of TN = tile_points(D) points in SoA order: tile t is one contiguous block
 //   [D+2][TN] fp32 = D rows of prescaled whitened coordinates + 1 row of normalised weights + 1 header
 //   row whose first 2D words are the tile's bounding box (lo[D], hi[D]),
 // so that ONE 1-D TMA bulk copy (cp.async.bulk, SASS UBLKCP) moves a whole tile into shared memory
 // and an LDS.128 of row k yields two packed {x_j, x_j+1} operands for FADD2/FFMA2.
 // Tiles are the leaves of a kd-tree over the training points (built on the host at fit time), so a
 // tile is spatially compact and its box test can prove that every pair term flushes to zero.
-#ifndef SKB_TN
-#define SKB_TN 128
+#ifndef SKB_TN_LO
+#define SKB_TN_LO 128
 #endif
-constexpr int TN = SKB_TN;           // training points per tile (kd leaf size)
+#ifndef SKB_TN_HI
+#define SKB_TN_HI 64
+#endif
+// training points per tile (= kd leaf size).  Smaller leaves have tighter boxes and cull more, which pays
+// in higher dimensions (measured d=8 +6 %, d=16 +14 % for 64 vs 128); below d=5 128 is as good or better.
+__host__ __device__ constexpr int tile_points(int D) { return D <= 4 ? SKB_TN_LO : SKB_TN_HI; }
 #ifndef SKB_NSTAGE
 #define SKB_NSTAGE 3
 #endif
@@ -65,11 +70,11 @@ __host__ __device__ constexpr int queries_per_thread(int D)
 // thread = more independent FMA chains and fewer LDS per pair.  A query's arithmetic does not depend on Q
 // (each query is a private register chain), so both variants give bit-identical results.
 __host__ __device__ constexpr int queries_per_thread_dense(int D) { return D <= 4 ? 8 : (D <= 8 ? 4 : 2); }
-__host__ __device__ constexpr int stage_floats(int D) { return (D + 2) * TN; }   // D coords, weights, header (box)
+__host__ __device__ constexpr int stage_floats(int D) { return (D + 2) * tile_points(D); }   // D coords, weights, header (box)
 
 // Device-resident description of one fitted KDE (one per handle, uploaded at skb_create).
 struct KdeDev {
-    const float* tiles;      // [ntiles][D+1][TN]
+    const float* tiles;      // [ntiles][D+2][tile_points(D)]
     const double* zt64;      // [N][D] whitened fp64 rows (draw centres)
     const double* cumsum_w;  // [N] sequential fp64 cumsum (NULL for unweighted)
     const float* boxes;      // [ntiles][2][D] lo / hi of the packed fp32 coordinates

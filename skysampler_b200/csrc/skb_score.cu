@@ -112,6 +112,7 @@ constexpr float CULL_MARGIN = 128.f;              // box lower bound this far pa
 // the training-side operands of one step: 4 points as two packed pairs per dimension (+ weights)
 template <int D>
 struct StepOperands {
+    static constexpr int TN = tile_points(D);
     u64 xa[D], xb[D], wa, wb;
     template <bool WITH_W>
     __device__ __forceinline__ void load(const float* __restrict__ tile, int j)
@@ -226,6 +227,7 @@ template <int D, int Q, bool MIN_ONLY>
 __device__ __forceinline__ void step_compute8(const float* __restrict__ tile, int j, const u64 (&q2)[Q][D],
                                               const u64 (&nm2)[Q], u64 (&sum2)[Q], float (&amin)[Q])
 {
+    constexpr int TN = tile_points(D);
     u64 xa[D], xb[D], xc[D], xd[D];
 #pragma unroll
     for (int k = 0; k < D; k++) {
@@ -380,6 +382,7 @@ __global__ void __launch_bounds__(NT, (Q == queries_per_thread(D) ? min_blocks_p
 skb_score_kernel(const __grid_constant__ ScoreLaunch L)
 {
     constexpr int QB = NT * Q;
+    constexpr int TN = tile_points(D);
     constexpr int STAGE_FLOATS = stage_floats(D);
     constexpr uint32_t STAGE_BYTES = STAGE_FLOATS * sizeof(float);
     constexpr int NWARP = NT / 32;
