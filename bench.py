@@ -398,8 +398,8 @@ def run_ours(args):
             except Exception:
                 traffic = None
         flop_pair = 3 * D + 1
-        # executed pairs: (64-point blocks x queries per thread, warp level) x 64 points x 32 lanes
-        exec_pairs_per_launch = st[1] * 64.0 * 32.0 / max(args.steps, 1)
+        # executed pairs: (query, point) pairs per lane counted at warp level x 32 lanes
+        exec_pairs_per_launch = st[1] * 32.0 / max(args.steps, 1)
         exec_frac = exec_pairs_per_launch / pairs_per_step_rank
         ach_exec = exec_pairs_per_launch / (kernel_ms * 1e-3)
         dense_rate = pairs_per_step_rank / (dense_ms * 1e-3)

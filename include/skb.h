@@ -195,8 +195,8 @@ int skb_measure_pipes(int device, double ms_each, double* fma_lane_per_s, double
 
 /*
  * Diagnostics of the score kernel since the last reset (synchronises the device):
- *   out4[0] = 64-point blocks re-run after an exponent-window overflow, x queries per thread (warp level)
- *   out4[1] = 64-point blocks evaluated x queries per thread (warp level): x 64 x 32 = pairs evaluated
+ *   out4[0] = (query, point) pairs per lane re-run after an exponent-window overflow (warp level)
+ *   out4[1] = (query, point) pairs per lane evaluated (warp level): x 32 lanes = pairs evaluated
  *   out4[2] = tiles skipped by the box tests (warp level);  out4[3] = tiles in range (warp level).
  */
 int skb_debug_counters(int device, uint64_t* out4, int reset);

@@ -19,20 +19,24 @@ typedef unsigned long long u64;
 #ifndef SKB_TN_LO
 #define SKB_TN_LO 128
 #endif
+#ifndef SKB_TN_MID
+#define SKB_TN_MID 64
+#endif
 #ifndef SKB_TN_HI
 #define SKB_TN_HI 64
 #endif
 // training points per tile (= kd leaf size).  Smaller leaves have tighter boxes and cull more, which pays
 // in higher dimensions (measured d=8 +6 %, d=16 +14 % for 64 vs 128); below d=5 128 is as good or better.
-__host__ __device__ constexpr int tile_points(int D) { return D <= 4 ? SKB_TN_LO : SKB_TN_HI; }
+__host__ __device__ constexpr int tile_points(int D) { return D <= 4 ? SKB_TN_LO : (D <= 8 ? SKB_TN_MID : SKB_TN_HI); }
 #ifndef SKB_NSTAGE
 #define SKB_NSTAGE 3
 #endif
 #ifndef SKB_NSTAGE_HI
 #define SKB_NSTAGE_HI 2
 #endif
-// TMA ring depth (shared memory per CTA = depth x tile bytes; D > 8 tiles are twice as large)
-__host__ __device__ constexpr int nstage(int D) { return D <= 8 ? SKB_NSTAGE : SKB_NSTAGE_HI; }
+// TMA ring depth (shared memory per CTA = depth x tile bytes).  D >= 5 runs the per-query inner loop, whose
+// speed follows the number of resident warps: two stages there keep 16 one-warp CTAs on an SM.
+__host__ __device__ constexpr int nstage(int D) { return D <= 4 ? SKB_NSTAGE : SKB_NSTAGE_HI; }
 #ifndef SKB_NT
 #define SKB_NT 32
 #endif

@@ -84,14 +84,14 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// diagnostics (warp level): [0] overflow re-runs of a 64-point block x queries per thread, [1] 64-point
-// blocks processed x queries per thread (x 64 x 32 = pairs evaluated), [2] tiles culled by the box tests,
-// [3] tiles in range
+// diagnostics (warp level): [0] (query, point) pairs per lane re-run after an exponent-window overflow,
+// [1] (query, point) pairs per lane evaluated (x 32 lanes = pairs evaluated), [2] tiles culled by the box
+// tests, [3] tiles in range
 __device__ unsigned long long g_stats[4];
 
 constexpr float OVERFLOW_LIMIT = 1.329228e36f;    // 2^120: a block partial sum at/above this is re-run
 constexpr float REF_BIAS = 90.f;                  // reference sits this many binades below the closest point seen
-constexpr int SUB = 64;                           // points per overflow-checked block
+constexpr int SUB_MAX = 64;                       // points per overflow-checked block (at most one tile)
 constexpr float CULL_MARGIN = 128.f;              // box lower bound this far past the reference => all terms flush to 0
 
 // ---------------------------------------------------------------------------------------------
@@ -375,14 +375,85 @@ __device__ __forceinline__ void finalize_query(const FinTable& fin, int first, i
 }
 
 // ---------------------------------------------------------------------------------------------
+// Per-query culling ("PQ") for D >= 5.  With lanes = queries a tile is evaluated for all 32 queries of the
+// warp as soon as ONE of them needs it; in 8-D a query needs ~1.2 % of the kd leaves but the union over a
+// warp's 32 Morton neighbours is ~5 %, so 3/4 of the evaluated pairs are terms that flush to zero.  The PQ
+// inner loop turns the warp around for the arithmetic: every lane keeps TWO training points of the 64-point
+// tile in registers (one packed fp32x2 operand per dimension), the box test is still one query per lane, and
+// the ballot of that test is walked bit by bit — only the queries that need the tile are evaluated, their
+// prescaled coordinates broadcast from shared memory.  Lane l adds its two terms to part[query][l] (fp32,
+// shared memory); rows are folded into the owner lane's fp64 (m, S) state at fixed tile-index boundaries
+// (every PQ_EPOCH tiles) in a fixed order, so a query's bits do not depend on its warp companions.
+// ---------------------------------------------------------------------------------------------
+#ifndef SKB_PQ
+#define SKB_PQ 1
+#endif
+#ifndef SKB_PQ_MINB_HI
+#define SKB_PQ_MINB_HI 16     // same for D > 8
+#endif
+#ifndef SKB_PQ_MIN_D
+#define SKB_PQ_MIN_D 6
+#endif
+#ifndef SKB_TEST_UNROLL
+#define SKB_TEST_UNROLL 4     // tile box tests of the need-bitmap phase in flight at once
+#endif
+#ifndef SKB_PQ_MINB
+#define SKB_PQ_MINB 16        // launch bound (CTAs per SM) of the PQ instantiations for D <= 8
+#endif
+constexpr int PQ_EPOCH_SHIFT = 7;                 // fp32 row partials are folded into fp64 every 128 tile indices
+constexpr int PQ_ROW = 33;                        // row stride of part[][] (floats): conflict-free row walks
+constexpr float PQ_LIMIT = 2.0679515e-25f;        // 2^-82 = 2^(8 - REF_BIAS): a point >= 8 binades closer than the reference
+__host__ __device__ constexpr bool pq_mode(int D, int Q) { return SKB_PQ && D >= SKB_PQ_MIN_D && Q == 1 && tile_points(D) == 64 && NT == 32; }
+__host__ __device__ constexpr int pq_qstride(int D) { return (D + 2) & ~1; }          // u64 words per query row ({z,z} x D, {-m,-m})
+__host__ __device__ constexpr size_t pq_smem_bytes(int D, int Q)
+{
+    return pq_mode(D, Q) ? (size_t)32 * pq_qstride(D) * 8 + (size_t)32 * PQ_ROW * 4 + 16 : 0;
+}
+
+// acc - m for this lane's two points against the query row in shared memory
+template <int D>
+__device__ __forceinline__ void pq_acc(const u64* __restrict__ qrow, const u64 (&p2)[D], float& a0, float& a1)
+{
+    constexpr int QS = pq_qstride(D);
+    u64 r[QS];
+#pragma unroll
+    for (int k = 0; k < QS; k += 2) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(qrow + k);
+        r[k] = v.x; r[k + 1] = v.y;
+    }
+    u64 acc = r[D];
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        const u64 dz = sub2(r[k], p2[k]);
+        acc = fma2(dz, dz, acc);
+    }
+    upk(acc, a0, a1);
+}
+
+// fold row `row` of the fp32 partials into a double, fixed order, and clear it
+__device__ __forceinline__ double pq_fold_row(float* __restrict__ part, int row)
+{
+    float* p = part + row * PQ_ROW;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int l = 0; l < 32; l += 4) {
+        s0 += (double)p[l]; s1 += (double)p[l + 1]; s2 += (double)p[l + 2]; s3 += (double)p[l + 3];
+        p[l] = 0.f; p[l + 1] = 0.f; p[l + 2] = 0.f; p[l + 3] = 0.f;
+    }
+    return __dadd_rn(__dadd_rn(s0, s1), __dadd_rn(s2, s3));
+}
+
+// ---------------------------------------------------------------------------------------------
 // The score kernel.  grid = (query blocks, jobs, training splits), block = NT threads.
 // ---------------------------------------------------------------------------------------------
 template <int D, int Q>
-__global__ void __launch_bounds__(NT, (Q == queries_per_thread(D) ? min_blocks_per_sm(D) : (D <= 4 ? 2 : (D <= 8 ? 3 : 4))) * (128 / NT))
+__global__ void __launch_bounds__(NT, pq_mode(D, Q) ? (D <= 8 ? SKB_PQ_MINB : SKB_PQ_MINB_HI)
+                                                    : (Q == queries_per_thread(D) ? min_blocks_per_sm(D) : (D <= 4 ? 2 : (D <= 8 ? 3 : 4))) * (128 / NT))
 skb_score_kernel(const __grid_constant__ ScoreLaunch L)
 {
     constexpr int QB = NT * Q;
     constexpr int TN = tile_points(D);
+    constexpr int SUB = TN < SUB_MAX ? TN : SUB_MAX;
     constexpr int STAGE_FLOATS = stage_floats(D);
     constexpr uint32_t STAGE_BYTES = STAGE_FLOATS * sizeof(float);
     constexpr int NWARP = NT / 32;
@@ -397,7 +468,11 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
     float* stages = reinterpret_cast<float*>(smem_raw);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NSTAGE * STAGE_BYTES);
     uint64_t* empty_bar = full_bar + NSTAGE;
-    unsigned* need_bits = reinterpret_cast<unsigned*>(empty_bar + NSTAGE);   // one bit per tile: some warp needs it
+    constexpr bool PQ = pq_mode(D, Q);
+    constexpr int QS = pq_qstride(D);
+    u64* pq_rows = reinterpret_cast<u64*>(empty_bar + NSTAGE);                // PQ: 32 query rows ({z,z} x D, {-m,-m})
+    float* pq_part = reinterpret_cast<float*>(pq_rows + (PQ ? 32 * QS : 0));  // PQ: part[query][lane]
+    unsigned* need_bits = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(empty_bar + NSTAGE) + pq_smem_bytes(D, Q));
     __shared__ int s_last[QB / FB];
 
     const int tid = threadIdx.x;
@@ -563,6 +638,13 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
         }
     }
 
+    if constexpr (PQ) {
+#pragma unroll
+        for (int k = 0; k < D; k++) pq_rows[tid * QS + k] = q2[0][k];
+        pq_rows[tid * QS + D] = nm2[0];
+        for (int l = 0; l < 32; l++) pq_part[tid * PQ_ROW + l] = 0.f;
+    }
+
     // ---- which tiles does this CTA need at all?  A tile that every warp can already cull with its initial
     // references is never requested from L2 (references only move down, so this is conservative).  Two
     // levels: a super-box that every query of the warp culls dismisses its SG tiles at once.
@@ -593,7 +675,8 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
             if (!__any_sync(0xffffffffu, need_s)) continue;
             unsigned word = 0u;                                        // SG = 16 tiles -> half a bitmap word
             const int tb = sidx * SG;
-#pragma unroll 1
+            constexpr int kTestUnroll = SKB_TEST_UNROLL;
+#pragma unroll kTestUnroll
             for (int b = 0; b < SG; b++) {
                 const int t = tb + b;
                 if (t < t0 || t >= t1) continue;
@@ -653,8 +736,11 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
         }
     }
 
+    int pq_epoch = -1;
+    unsigned long long n_pq_pairs = 0;
     for (int it = 0;; it++) {
-        if (next_tile(cw, cbits) < 0) break;
+        const int tcur = next_tile(cw, cbits);
+        if (tcur < 0) break;
         n_visited++;
         const int s = it % NSTAGE;
         const uint32_t ph = (it / NSTAGE) & 1;
@@ -672,6 +758,96 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
         __syncwarp();
         mbar_wait(&full_bar[s], ph);
         const float* tile = stages + (size_t)s * STAGE_FLOATS;
+
+        if constexpr (PQ) {
+            const float* hdr = tile + (D + 1) * TN;
+            bool need = true;
+            if (job.cull) {
+                float lb = 0.f;
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    float zq, dup; upk(q2[0][k], zq, dup);
+                    const float gap = fmaxf(fmaxf(hdr[k] - zq, zq - hdr[D + k]), 0.f);
+                    lb = fmaf(gap, gap, lb);
+                }
+                need = !(lb - mref[0] > CULL_MARGIN);
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, need);
+            if (mask == 0u) {
+                if (lane == 0) mbar_arrive(&empty_bar[s]);
+                n_culled++;
+                continue;
+            }
+            const int epoch = (t0 + tcur) >> PQ_EPOCH_SHIFT;
+            if (epoch != pq_epoch) {
+                if (pq_epoch >= 0) { __syncwarp(); S[0] += pq_fold_row(pq_part, lane); __syncwarp(); }
+                pq_epoch = epoch;
+            }
+            // this lane's two points of the tile
+            u64 p2[D];
+#pragma unroll
+            for (int k = 0; k < D; k++) p2[k] = *reinterpret_cast<const u64*>(tile + k * TN + 2 * lane);
+            float w0, w1;
+            upk(*reinterpret_cast<const u64*>(tile + D * TN + 2 * lane), w0, w1);
+            n_pq_pairs += 2u * __popc(mask);
+
+            // rare: a point >= 8 binades closer than the reference was built for (or a NaN row) — fold the
+            // row, move the query's reference to the tile's closest point, re-evaluate
+            auto recentre = [&](int i, float a0, float a1) -> float {
+                float am = fminf(a0, a1);
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) am = fminf(am, __shfl_xor_sync(0xffffffffu, am, off));
+                const float delta = floorf(am) - REF_BIAS;
+                n_rerun++;
+                if (delta < 0.f && delta > -1.0e30f) {
+                    __syncwarp();
+                    if (lane == i) {
+                        S[0] += pq_fold_row(pq_part, i);
+                        S[0] = ldexp(S[0], (int)fmaxf(delta, -4000.f));
+                        mref[0] += delta;
+                        nm2[0] = pk(-mref[0], -mref[0]);
+                        pq_rows[i * QS + D] = nm2[0];
+                    }
+                    __syncwarp();
+                    pq_acc<D>(pq_rows + i * QS, p2, a0, a1);
+                    return __fmaf_rn(w1, ex2_neg(a1), __fmul_rn(w0, ex2_neg(a0)));
+                }
+                if (lane == i) S[0] = NAN;                                  // NaN / inf query row: propagate
+                return 0.f;
+            };
+
+            while (mask) {
+                const int i0 = __ffs(mask) - 1;
+                mask &= mask - 1u;
+                if (mask) {
+                    const int i1 = __ffs(mask) - 1;
+                    mask &= mask - 1u;
+                    float a0, a1, b0, b1;
+                    float pa = pq_part[i0 * PQ_ROW + lane];                 // issued early: off the critical path
+                    float pb = pq_part[i1 * PQ_ROW + lane];
+                    pq_acc<D>(pq_rows + i0 * QS, p2, a0, a1);
+                    pq_acc<D>(pq_rows + i1 * QS, p2, b0, b1);
+                    float ta = __fmaf_rn(w1, ex2_neg(a1), __fmul_rn(w0, ex2_neg(a0)));
+                    float tb = __fmaf_rn(w1, ex2_neg(b1), __fmul_rn(w0, ex2_neg(b0)));
+                    if (__any_sync(0xffffffffu, !(ta < PQ_LIMIT) || !(tb < PQ_LIMIT))) {
+                        if (__any_sync(0xffffffffu, !(ta < PQ_LIMIT))) { ta = recentre(i0, a0, a1); pa = pq_part[i0 * PQ_ROW + lane]; }
+                        if (__any_sync(0xffffffffu, !(tb < PQ_LIMIT))) { tb = recentre(i1, b0, b1); pb = pq_part[i1 * PQ_ROW + lane]; }
+                    }
+                    pq_part[i0 * PQ_ROW + lane] = pa + ta;
+                    pq_part[i1 * PQ_ROW + lane] = pb + tb;
+                } else {
+                    float a0, a1;
+                    float pa = pq_part[i0 * PQ_ROW + lane];
+                    pq_acc<D>(pq_rows + i0 * QS, p2, a0, a1);
+                    float ta = __fmaf_rn(w1, ex2_neg(a1), __fmul_rn(w0, ex2_neg(a0)));
+                    if (__any_sync(0xffffffffu, !(ta < PQ_LIMIT))) { ta = recentre(i0, a0, a1); pa = pq_part[i0 * PQ_ROW + lane]; }
+                    pq_part[i0 * PQ_ROW + lane] = pa + ta;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+            continue;
+        }
 
         u64 sum2[Q];
         float amin[Q];
@@ -772,9 +948,14 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
         if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
 
+    if constexpr (PQ) {
+        __syncwarp();
+        S[0] += pq_fold_row(pq_part, lane);
+    }
+
     if (lane == 0) {
-        if (n_rerun) atomicAdd(&g_stats[0], (unsigned long long)n_rerun * Q);
-        atomicAdd(&g_stats[1], (unsigned long long)n_blocks * Q);
+        if (n_rerun) atomicAdd(&g_stats[0], (unsigned long long)n_rerun * (PQ ? 2 : Q * SUB));
+        atomicAdd(&g_stats[1], PQ ? n_pq_pairs : (unsigned long long)n_blocks * Q * SUB);
         atomicAdd(&g_stats[2], (unsigned long long)(n_culled + (unsigned)ntl - n_visited));
         atomicAdd(&g_stats[3], (unsigned long long)ntl);      // tiles of the split (culled = box-culled at either level)
     }
@@ -831,7 +1012,7 @@ static cudaError_t launch_score_dq(const ScoreLaunch& L, int njobs, long long ma
 {
     constexpr int NSTAGE = nstage(D);
     const size_t smem = (size_t)NSTAGE * stage_floats(D) * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t) +
-                        (((size_t)max_ntiles + 31) / 32) * 4 + 16;
+                        pq_smem_bytes(D, Q) + (((size_t)max_ntiles + 31) / 32) * 4 + 16;
     cudaError_t e = cudaFuncSetAttribute(skb_score_kernel<D, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)max_qblocks, (unsigned)njobs, (unsigned)max_split);
@@ -854,7 +1035,8 @@ template <int D, int Q>
 static int occupancy_dq()
 {
     constexpr int NSTAGE = nstage(D);
-    const size_t smem = (size_t)NSTAGE * stage_floats(D) * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t) + 1024;
+    const size_t smem = (size_t)NSTAGE * stage_floats(D) * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t) +
+                        pq_smem_bytes(D, Q) + 1024;
     int n = 0;
     if (cudaFuncSetAttribute(skb_score_kernel<D, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, skb_score_kernel<D, Q>, NT, smem) != cudaSuccess) {
