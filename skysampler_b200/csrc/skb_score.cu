@@ -374,127 +374,11 @@ __device__ __forceinline__ void finalize_query(const FinTable& fin, int first, i
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Per-query culling ("PQ") for D >= 5.  With lanes = queries a tile is evaluated for all 32 queries of the
-// warp as soon as ONE of them needs it; in 8-D a query needs ~1.2 % of the kd leaves but the union over a
-// warp's 32 Morton neighbours is ~5 %, so 3/4 of the evaluated pairs are terms that flush to zero.  The PQ
-// inner loop turns the warp around for the arithmetic: every lane keeps TWO training points of the 64-point
-// tile in registers (one packed fp32x2 operand per dimension), the box test is still one query per lane, and
-// the ballot of that test is walked bit by bit — only the queries that need the tile are evaluated, their
-// prescaled coordinates broadcast from shared memory.  Lane l adds its two terms to part[query][l] (fp32,
-// shared memory); rows are folded into the owner lane's fp64 (m, S) state at fixed tile-index boundaries
-// (every PQ_EPOCH tiles) in a fixed order, so a query's bits do not depend on its warp companions.
-// ---------------------------------------------------------------------------------------------
-#ifndef SKB_PQ
-#define SKB_PQ 1
-#endif
-#ifndef SKB_PQ_MINB_HI
-#define SKB_PQ_MINB_HI 16     // same for D > 8
-#endif
-#ifndef SKB_PQ_MIN_D
-#define SKB_PQ_MIN_D 6
-#endif
-#ifndef SKB_TEST_UNROLL
-#define SKB_TEST_UNROLL 4     // tile box tests of the need-bitmap phase in flight at once
-#endif
-#ifndef SKB_PQ_MINB
-#define SKB_PQ_MINB 16        // launch bound (CTAs per SM) of the PQ instantiations for D <= 8
-#endif
-constexpr int PQ_EPOCH_SHIFT = 7;                 // fp32 row partials are folded into fp64 every 128 tile indices
-constexpr int PQ_ROW = 33;                        // row stride of part[][] (floats): conflict-free row walks
-constexpr float PQ_LIMIT = 2.0679515e-25f;        // 2^-82 = 2^(8 - REF_BIAS): a point >= 8 binades closer than the reference
-__host__ __device__ constexpr bool pq_mode(int D, int Q) { return SKB_PQ && D >= SKB_PQ_MIN_D && Q == 1 && tile_points(D) == 64 && NT == 32; }
-__host__ __device__ constexpr int pq_qstride(int D) { return (D + 2) & ~1; }          // u64 words per query row ({z,z} x D, {-m,-m})
-__host__ __device__ constexpr size_t pq_smem_bytes(int D, int Q)
-{
-    return pq_mode(D, Q) ? (size_t)32 * pq_qstride(D) * 8 + (size_t)32 * PQ_ROW * 4 + 16 : 0;
-}
-
-// acc - m for this lane's two points against the query row in shared memory
-template <int D>
-__device__ __forceinline__ void pq_acc(const u64* __restrict__ qrow, const u64 (&p2)[D], float& a0, float& a1)
-{
-    constexpr int QS = pq_qstride(D);
-    u64 r[QS];
-#pragma unroll
-    for (int k = 0; k < QS; k += 2) {
-        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(qrow + k);
-        r[k] = v.x; r[k + 1] = v.y;
-    }
-    u64 acc = r[D];
-#pragma unroll
-    for (int k = 0; k < D; k++) {
-        const u64 dz = sub2(r[k], p2[k]);
-        acc = fma2(dz, dz, acc);
-    }
-    upk(acc, a0, a1);
-}
-
-// fold row `row` of the fp32 partials into a double, fixed order, and clear it
-__device__ __forceinline__ double pq_fold_row(float* __restrict__ part, int row)
-{
-    float* p = part + row * PQ_ROW;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-    for (int l = 0; l < 32; l += 4) {
-        s0 += (double)p[l]; s1 += (double)p[l + 1]; s2 += (double)p[l + 2]; s3 += (double)p[l + 3];
-        p[l] = 0.f; p[l + 1] = 0.f; p[l + 2] = 0.f; p[l + 3] = 0.f;
-    }
-    return __dadd_rn(__dadd_rn(s0, s1), __dadd_rn(s2, s3));
-}
-
-// ---------------------------------------------------------------------------------------------
-// The score kernel.  grid = (query blocks, jobs, training splits), block = NT threads.
-// ---------------------------------------------------------------------------------------------
+// ---- load this thread's Q query rows, whiten + prescale in fp64, pack as {z, z} ----
 template <int D, int Q>
-__global__ void __launch_bounds__(NT, pq_mode(D, Q) ? (D <= 8 ? SKB_PQ_MINB : SKB_PQ_MINB_HI)
-                                                    : (Q == queries_per_thread(D) ? min_blocks_per_sm(D) : (D <= 4 ? 2 : (D <= 8 ? 3 : 4))) * (128 / NT))
-skb_score_kernel(const __grid_constant__ ScoreLaunch L)
+__device__ __forceinline__ void load_queries(const ScoreJob& job, const KdeDev* __restrict__ kde, long long qbase, int tid,
+                                             long long M, u64 (&q2)[Q][D])
 {
-    constexpr int QB = NT * Q;
-    constexpr int TN = tile_points(D);
-    constexpr int SUB = TN < SUB_MAX ? TN : SUB_MAX;
-    constexpr int STAGE_FLOATS = stage_floats(D);
-    constexpr uint32_t STAGE_BYTES = STAGE_FLOATS * sizeof(float);
-    constexpr int NWARP = NT / 32;
-    constexpr int NSTAGE = nstage(D);
-
-    const ScoreJob& job = L.jobs[blockIdx.y];
-    const long long M = job.M;
-    const long long qbase = (long long)blockIdx.x * QB;
-    if (qbase >= M || (int)blockIdx.z >= job.nsplit) return;
-
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* stages = reinterpret_cast<float*>(smem_raw);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NSTAGE * STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + NSTAGE;
-    constexpr bool PQ = pq_mode(D, Q);
-    constexpr int QS = pq_qstride(D);
-    u64* pq_rows = reinterpret_cast<u64*>(empty_bar + NSTAGE);                // PQ: 32 query rows ({z,z} x D, {-m,-m})
-    float* pq_part = reinterpret_cast<float*>(pq_rows + (PQ ? 32 * QS : 0));  // PQ: part[query][lane]
-    unsigned* need_bits = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(empty_bar + NSTAGE) + pq_smem_bytes(D, Q));
-    __shared__ int s_last[QB / FB];
-
-    const int tid = threadIdx.x;
-    const KdeDev* __restrict__ kde = job.kde;
-    const int ntiles = kde->ntiles;
-    const int nsplit = job.nsplit;
-    const int t0 = (int)(((long long)ntiles * blockIdx.z) / nsplit);
-    const int t1 = (int)(((long long)ntiles * (blockIdx.z + 1)) / nsplit);
-    const int ntl = t1 - t0;
-    const float* __restrict__ gtiles = kde->tiles + (size_t)t0 * STAGE_FLOATS;
-
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < NSTAGE; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NWARP); }
-        mbar_fence_init();
-    }
-    const int nwords = (ntl + 31) >> 5;
-    for (int w = tid; w < nwords; w += NT) need_bits[w] = 0u;
-    __syncthreads();
-
-    // ---- prologue: load this thread's Q query rows, whiten + prescale in fp64, pack as {z, z} ----
-    u64 q2[Q][D];
     {
         const double c = kde->c;
 #pragma unroll
@@ -545,30 +429,21 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
             }
         }
     }
+}
 
-    // ---- main loop over this split's tiles -----------------------------------------------------
-    // Reference exponent window.  Pair terms are t = 2^(mref - acc) in fp32 (flush below 2^-126,
-    // overflow above 2^127).  The log-sum is carried by terms within ~30 binades of the closest
-    // point, so any mref in (acc_min - 96, acc_min + 120) is exact to fp32 rounding.  mref is set to
-    // (smallest acc seen) - REF_BIAS: points up to ~210 binades closer than anything seen so far are
-    // absorbed without action; beyond that the SUB-point block overflows and is re-run once.
-    float mref[Q];          // integer-valued reference exponent per query
-    double S[Q];            // fp64 running sum at reference mref:  sum_j w_j 2^(-acc_j) = S * 2^(-mref)
-    u64 nm2[Q];
-#pragma unroll
-    for (int q = 0; q < Q; q++) { mref[q] = 0.f; S[q] = 0.0; nm2[q] = pk(0.f, 0.f); }
-
-    const int lane = tid & 31;
-    unsigned n_rerun = 0, n_blocks = 0, n_culled = 0, n_visited = 0;
-
-    // Reference exponents, per query and independent of split / batch / GPU:
-    //  (1) nearest super-box (SG consecutive kd leaves) by box distance, then the nearest tile box inside
-    //      it: the query's "home" tile;
-    //  (2) the home tile is evaluated exactly (min-only, straight from L2).  A real point's distance is an
-    //      upper bound of the true minimum, and the true nearest neighbour usually lives in the home tile,
-    //      so the reference is tight from the first tile on — tight references are what lets the box test
-    //      cull.  (If a closer point turns up later the reference is tightened / recentred on the fly.)
-    float bmin[Q];          // running estimate of the smallest acc seen (absolute)
+// Reference exponents, per query and independent of split / batch / GPU:
+//  (1) nearest super-box (SG consecutive kd leaves) by box distance, then the nearest tile box inside
+//      it: the query's "home" tile;
+//  (2) the home tile is evaluated exactly (min-only, straight from L2).  A real point's distance is an
+//      upper bound of the true minimum, and the true nearest neighbour usually lives in the home tile,
+//      so the reference is tight from the first tile on — tight references are what lets the box test
+//      cull.  (If a closer point turns up later the reference is tightened / recentred on the fly.)
+template <int D, int Q>
+__device__ __forceinline__ void home_reference(const KdeDev* __restrict__ kde, int ntiles, const u64 (&q2)[Q][D],
+                                               float (&bmin)[Q], float (&mref)[Q], u64 (&nm2)[Q])
+{
+    constexpr int TN = tile_points(D);
+    constexpr int STAGE_FLOATS = stage_floats(D);
     {
         const float* __restrict__ sbx = kde->sboxes;
         const float* __restrict__ bx = kde->boxes;
@@ -637,13 +512,207 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
             nm2[q] = pk(-m, -m);
         }
     }
+}
 
-    if constexpr (PQ) {
+// ---- epilogue: finalize from registers, or publish the partial state and let the last-arriving CTA of a
+// finalize block merge splits / form the ratio + accept ----
+template <int D, int Q>
+__device__ __forceinline__ void finish_queries(const ScoreLaunch& L, const ScoreJob& job, long long qbase, int tid, long long M,
+                                               const float (&mref)[Q], const double (&S)[Q], int* s_last)
+{
+    constexpr int QB = NT * Q;
+    const FinJob& myfin = L.fin.fj[job.fin_slot];
+    if (job.counters == nullptr) {
+        // single split, ungrouped: finalize straight from registers
 #pragma unroll
-        for (int k = 0; k < D; k++) pq_rows[tid * QS + k] = q2[0][k];
-        pq_rows[tid * QS + D] = nm2[0];
-        for (int l = 0; l < 32; l++) pq_part[tid * PQ_ROW + l] = 0.f;
+        for (int q = 0; q < Q; q++) {
+            const long long v = qbase + (long long)tid * Q + q;          // position in the visit order
+            if (v < M) {
+                const long long r = job.perm ? job.perm[v] : v;          // row of the query table
+                if (myfin.out_m) { myfin.out_m[r] = myfin.log_wmax - (double)mref[q] * LN2; myfin.out_s[r] = S[q]; }
+                if (myfin.out_logp) myfin.out_logp[r] = final_logp(myfin.log_norm, S[q], (double)mref[q]);
+            }
+        }
+        return;
     }
+    // partial states and arrival counters are indexed by visit-order position (shared by a group)
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        const long long v = qbase + (long long)tid * Q + q;
+        if (v < M) myfin.partial[(long long)blockIdx.z * M + v] = make_double2((double)mref[q], S[q]);
+    }
+    // last-arriving CTA of each finalize block (FB queries) merges splits / forms the ratio + accept
+    __threadfence();
+    __syncthreads();
+    if (tid < QB / FB) {
+        const long long fb = qbase / FB + tid;
+        int last = 0;
+        if (fb * FB < M) {
+            const int prev = atomicAdd(&job.counters[fb], 1);
+            last = (prev == job.expected - 1);
+            if (last) job.counters[fb] = 0;             // self-reset for the next call
+        }
+        s_last[tid] = last;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int b = 0; b < QB / FB; b++) {
+        if (!s_last[b]) continue;
+        __threadfence();
+        for (int i = tid; i < FB; i += NT) {
+            const long long r = qbase + (long long)b * FB + i;
+            if (r < M) finalize_query(L.fin, job.fin_first, job.fin_count, M, r);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-query culling ("PQ") kernel for D >= SKB_PQ_MIN_D.  With lanes = queries a tile is evaluated for all 32
+// queries of the warp as soon as ONE of them needs it; in 8-D a query needs ~1.2 % of the kd leaves but the
+// union over a warp's 32 Morton neighbours is ~5 %, so 3/4 of the pairs evaluated that way are terms that
+// flush to zero.  This kernel turns the warp around:
+//   * the training side is walked in chunks of PQ_CH super-boxes (PQ_CH * SG tiles).  Per chunk, one query
+//     per lane tests the super-boxes (ballot = which queries need it); then one TILE per lane tests its box
+//     against exactly those queries (coordinates broadcast from shared memory) and the non-empty
+//     (tile, query mask) pairs are compacted into a work list in shared memory;
+//   * the work list is streamed through the TMA ring.  Every lane keeps TWO training points of the 64-point
+//     tile in registers (one packed fp32x2 operand per dimension) and the tile's query mask is walked bit by
+//     bit: only the queries that need the tile are evaluated.  Lane l adds its two terms to part[query][l]
+//     (fp32, shared memory); rows are folded into the owner lane's fp64 (m, S) state at fixed tile-index
+//     boundaries (every 2^PQ_EPOCH_SHIFT tiles) in a fixed order.
+// A query's arithmetic depends on its own coordinates and the fitted KDE only (masks, references, fold points
+// are all functions of the query alone), so results stay bit-identical under any batching or sharding.
+// ---------------------------------------------------------------------------------------------
+#ifndef SKB_PQ
+#define SKB_PQ 1
+#endif
+#ifndef SKB_TEST_UNROLL
+#define SKB_TEST_UNROLL 4     // tile box tests of the need-bitmap phase (lanes = queries kernel) in flight at once
+#endif
+#ifndef SKB_PQ_MIN_D
+#define SKB_PQ_MIN_D 6
+#endif
+#ifndef SKB_PQ_MINB
+#define SKB_PQ_MINB 16        // launch bound (CTAs per SM) of the PQ kernel for D <= 8
+#endif
+#ifndef SKB_PQ_MINB_HI
+#define SKB_PQ_MINB_HI 16     // same for D > 8
+#endif
+#ifndef SKB_PQ_CH
+#define SKB_PQ_CH 16          // super-boxes per chunk (<= 32)
+#endif
+constexpr int PQ_CH = SKB_PQ_CH;
+constexpr int PQ_CAP = PQ_CH * SG;                // work-list capacity: every tile of a chunk
+constexpr int PQ_EPOCH_SHIFT = 7;                 // fp32 row partials are folded into fp64 every 128 tile indices
+constexpr int PQ_ROW = 33;                        // row stride of part[][] (floats): conflict-free row walks
+constexpr float PQ_LIMIT = 2.0679515e-25f;        // 2^-82 = 2^(8 - REF_BIAS): a point >= 8 binades closer than the reference
+static_assert(PQ_CH <= 32 && PQ_CAP <= 65536 && SG == 16, "PQ chunk layout");
+__host__ __device__ constexpr bool pq_mode(int D, int Q) { return SKB_PQ && D >= SKB_PQ_MIN_D && Q == 1 && tile_points(D) == 64; }
+__host__ __device__ constexpr int pq_qstride(int D) { return (D + 2) & ~1; }          // u64 words per query row ({z,z} x D, {-m,-m})
+__host__ __device__ constexpr size_t pq_smem_bytes(int D)
+{
+    return (size_t)nstage(D) * stage_floats(D) * 4 + (size_t)nstage(D) * 16 + (size_t)32 * pq_qstride(D) * 8 +
+           (size_t)32 * PQ_ROW * 4 + (size_t)PQ_CAP * 4 + (size_t)PQ_CAP * 2 + 16;
+}
+
+// acc - m for this lane's two points against the query row in shared memory
+template <int D>
+__device__ __forceinline__ void pq_acc(const u64* __restrict__ qrow, const u64 (&p2)[D], float& a0, float& a1)
+{
+    constexpr int QS = pq_qstride(D);
+    u64 r[QS];
+#pragma unroll
+    for (int k = 0; k < QS; k += 2) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(qrow + k);
+        r[k] = v.x; r[k + 1] = v.y;
+    }
+    u64 acc = r[D];
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        const u64 dz = sub2(r[k], p2[k]);
+        acc = fma2(dz, dz, acc);
+    }
+    upk(acc, a0, a1);
+}
+
+// fold row `row` of the fp32 partials into a double, fixed order, and clear it
+__device__ __forceinline__ double pq_fold_row(float* __restrict__ part, int row)
+{
+    float* p = part + row * PQ_ROW;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int l = 0; l < 32; l += 4) {
+        s0 += (double)p[l]; s1 += (double)p[l + 1]; s2 += (double)p[l + 2]; s3 += (double)p[l + 3];
+        p[l] = 0.f; p[l + 1] = 0.f; p[l + 2] = 0.f; p[l + 3] = 0.f;
+    }
+    return __dadd_rn(__dadd_rn(s0, s1), __dadd_rn(s2, s3));
+}
+
+// ---------------------------------------------------------------------------------------------
+// The score kernel.  grid = (query blocks, jobs, training splits), block = NT threads.
+// ---------------------------------------------------------------------------------------------
+template <int D, int Q>
+__global__ void __launch_bounds__(NT, (Q == queries_per_thread(D) ? min_blocks_per_sm(D) : (D <= 4 ? 2 : (D <= 8 ? 3 : 4))) * (128 / NT))
+skb_score_kernel(const __grid_constant__ ScoreLaunch L)
+{
+    constexpr int QB = NT * Q;
+    constexpr int TN = tile_points(D);
+    constexpr int SUB = TN < SUB_MAX ? TN : SUB_MAX;
+    constexpr int STAGE_FLOATS = stage_floats(D);
+    constexpr uint32_t STAGE_BYTES = STAGE_FLOATS * sizeof(float);
+    constexpr int NWARP = NT / 32;
+    constexpr int NSTAGE = nstage(D);
+
+    const ScoreJob& job = L.jobs[blockIdx.y];
+    const long long M = job.M;
+    const long long qbase = (long long)blockIdx.x * QB;
+    if (qbase >= M || (int)blockIdx.z >= job.nsplit) return;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* stages = reinterpret_cast<float*>(smem_raw);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NSTAGE * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + NSTAGE;
+    unsigned* need_bits = reinterpret_cast<unsigned*>(empty_bar + NSTAGE);   // one bit per tile: some warp needs it
+    __shared__ int s_last[QB / FB];
+
+    const int tid = threadIdx.x;
+    const KdeDev* __restrict__ kde = job.kde;
+    const int ntiles = kde->ntiles;
+    const int nsplit = job.nsplit;
+    const int t0 = (int)(((long long)ntiles * blockIdx.z) / nsplit);
+    const int t1 = (int)(((long long)ntiles * (blockIdx.z + 1)) / nsplit);
+    const int ntl = t1 - t0;
+    const float* __restrict__ gtiles = kde->tiles + (size_t)t0 * STAGE_FLOATS;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NWARP); }
+        mbar_fence_init();
+    }
+    const int nwords = (ntl + 31) >> 5;
+    for (int w = tid; w < nwords; w += NT) need_bits[w] = 0u;
+    __syncthreads();
+
+    u64 q2[Q][D];
+    load_queries<D, Q>(job, kde, qbase, tid, M, q2);
+
+    // ---- main loop over this split's tiles -----------------------------------------------------
+    // Reference exponent window.  Pair terms are t = 2^(mref - acc) in fp32 (flush below 2^-126,
+    // overflow above 2^127).  The log-sum is carried by terms within ~30 binades of the closest
+    // point, so any mref in (acc_min - 96, acc_min + 120) is exact to fp32 rounding.  mref is set to
+    // (smallest acc seen) - REF_BIAS: points up to ~210 binades closer than anything seen so far are
+    // absorbed without action; beyond that the SUB-point block overflows and is re-run once.
+    float mref[Q];          // integer-valued reference exponent per query
+    double S[Q];            // fp64 running sum at reference mref:  sum_j w_j 2^(-acc_j) = S * 2^(-mref)
+    u64 nm2[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) { mref[q] = 0.f; S[q] = 0.0; nm2[q] = pk(0.f, 0.f); }
+
+    const int lane = tid & 31;
+    unsigned n_rerun = 0, n_blocks = 0, n_culled = 0, n_visited = 0;
+
+    float bmin[Q];          // running estimate of the smallest acc seen (absolute)
+    home_reference<D, Q>(kde, ntiles, q2, bmin, mref, nm2);
 
     // ---- which tiles does this CTA need at all?  A tile that every warp can already cull with its initial
     // references is never requested from L2 (references only move down, so this is conservative).  Two
@@ -736,11 +805,8 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
         }
     }
 
-    int pq_epoch = -1;
-    unsigned long long n_pq_pairs = 0;
     for (int it = 0;; it++) {
-        const int tcur = next_tile(cw, cbits);
-        if (tcur < 0) break;
+        if (next_tile(cw, cbits) < 0) break;
         n_visited++;
         const int s = it % NSTAGE;
         const uint32_t ph = (it / NSTAGE) & 1;
@@ -758,96 +824,6 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
         __syncwarp();
         mbar_wait(&full_bar[s], ph);
         const float* tile = stages + (size_t)s * STAGE_FLOATS;
-
-        if constexpr (PQ) {
-            const float* hdr = tile + (D + 1) * TN;
-            bool need = true;
-            if (job.cull) {
-                float lb = 0.f;
-#pragma unroll
-                for (int k = 0; k < D; k++) {
-                    float zq, dup; upk(q2[0][k], zq, dup);
-                    const float gap = fmaxf(fmaxf(hdr[k] - zq, zq - hdr[D + k]), 0.f);
-                    lb = fmaf(gap, gap, lb);
-                }
-                need = !(lb - mref[0] > CULL_MARGIN);
-            }
-            unsigned mask = __ballot_sync(0xffffffffu, need);
-            if (mask == 0u) {
-                if (lane == 0) mbar_arrive(&empty_bar[s]);
-                n_culled++;
-                continue;
-            }
-            const int epoch = (t0 + tcur) >> PQ_EPOCH_SHIFT;
-            if (epoch != pq_epoch) {
-                if (pq_epoch >= 0) { __syncwarp(); S[0] += pq_fold_row(pq_part, lane); __syncwarp(); }
-                pq_epoch = epoch;
-            }
-            // this lane's two points of the tile
-            u64 p2[D];
-#pragma unroll
-            for (int k = 0; k < D; k++) p2[k] = *reinterpret_cast<const u64*>(tile + k * TN + 2 * lane);
-            float w0, w1;
-            upk(*reinterpret_cast<const u64*>(tile + D * TN + 2 * lane), w0, w1);
-            n_pq_pairs += 2u * __popc(mask);
-
-            // rare: a point >= 8 binades closer than the reference was built for (or a NaN row) — fold the
-            // row, move the query's reference to the tile's closest point, re-evaluate
-            auto recentre = [&](int i, float a0, float a1) -> float {
-                float am = fminf(a0, a1);
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) am = fminf(am, __shfl_xor_sync(0xffffffffu, am, off));
-                const float delta = floorf(am) - REF_BIAS;
-                n_rerun++;
-                if (delta < 0.f && delta > -1.0e30f) {
-                    __syncwarp();
-                    if (lane == i) {
-                        S[0] += pq_fold_row(pq_part, i);
-                        S[0] = ldexp(S[0], (int)fmaxf(delta, -4000.f));
-                        mref[0] += delta;
-                        nm2[0] = pk(-mref[0], -mref[0]);
-                        pq_rows[i * QS + D] = nm2[0];
-                    }
-                    __syncwarp();
-                    pq_acc<D>(pq_rows + i * QS, p2, a0, a1);
-                    return __fmaf_rn(w1, ex2_neg(a1), __fmul_rn(w0, ex2_neg(a0)));
-                }
-                if (lane == i) S[0] = NAN;                                  // NaN / inf query row: propagate
-                return 0.f;
-            };
-
-            while (mask) {
-                const int i0 = __ffs(mask) - 1;
-                mask &= mask - 1u;
-                if (mask) {
-                    const int i1 = __ffs(mask) - 1;
-                    mask &= mask - 1u;
-                    float a0, a1, b0, b1;
-                    float pa = pq_part[i0 * PQ_ROW + lane];                 // issued early: off the critical path
-                    float pb = pq_part[i1 * PQ_ROW + lane];
-                    pq_acc<D>(pq_rows + i0 * QS, p2, a0, a1);
-                    pq_acc<D>(pq_rows + i1 * QS, p2, b0, b1);
-                    float ta = __fmaf_rn(w1, ex2_neg(a1), __fmul_rn(w0, ex2_neg(a0)));
-                    float tb = __fmaf_rn(w1, ex2_neg(b1), __fmul_rn(w0, ex2_neg(b0)));
-                    if (__any_sync(0xffffffffu, !(ta < PQ_LIMIT) || !(tb < PQ_LIMIT))) {
-                        if (__any_sync(0xffffffffu, !(ta < PQ_LIMIT))) { ta = recentre(i0, a0, a1); pa = pq_part[i0 * PQ_ROW + lane]; }
-                        if (__any_sync(0xffffffffu, !(tb < PQ_LIMIT))) { tb = recentre(i1, b0, b1); pb = pq_part[i1 * PQ_ROW + lane]; }
-                    }
-                    pq_part[i0 * PQ_ROW + lane] = pa + ta;
-                    pq_part[i1 * PQ_ROW + lane] = pb + tb;
-                } else {
-                    float a0, a1;
-                    float pa = pq_part[i0 * PQ_ROW + lane];
-                    pq_acc<D>(pq_rows + i0 * QS, p2, a0, a1);
-                    float ta = __fmaf_rn(w1, ex2_neg(a1), __fmul_rn(w0, ex2_neg(a0)));
-                    if (__any_sync(0xffffffffu, !(ta < PQ_LIMIT))) { ta = recentre(i0, a0, a1); pa = pq_part[i0 * PQ_ROW + lane]; }
-                    pq_part[i0 * PQ_ROW + lane] = pa + ta;
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[s]);
-            continue;
-        }
 
         u64 sum2[Q];
         float amin[Q];
@@ -948,75 +924,294 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
         if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
 
-    if constexpr (PQ) {
-        __syncwarp();
-        S[0] += pq_fold_row(pq_part, lane);
-    }
-
     if (lane == 0) {
-        if (n_rerun) atomicAdd(&g_stats[0], (unsigned long long)n_rerun * (PQ ? 2 : Q * SUB));
-        atomicAdd(&g_stats[1], PQ ? n_pq_pairs : (unsigned long long)n_blocks * Q * SUB);
+        if (n_rerun) atomicAdd(&g_stats[0], (unsigned long long)n_rerun * Q * SUB);
+        atomicAdd(&g_stats[1], (unsigned long long)n_blocks * Q * SUB);
         atomicAdd(&g_stats[2], (unsigned long long)(n_culled + (unsigned)ntl - n_visited));
         atomicAdd(&g_stats[3], (unsigned long long)ntl);      // tiles of the split (culled = box-culled at either level)
     }
 
-    // ---- epilogue ------------------------------------------------------------------------------
-    const FinJob& myfin = L.fin.fj[job.fin_slot];
-    if (job.counters == nullptr) {
-        // single split, ungrouped: finalize straight from registers
+    finish_queries<D, Q>(L, job, qbase, tid, M, mref, S, s_last);
+}
+
+template <int D>
+__global__ void __launch_bounds__(32, D <= 8 ? SKB_PQ_MINB : SKB_PQ_MINB_HI)
+skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
+{
+    constexpr int Q = 1;
+    constexpr int TN = tile_points(D);
+    constexpr int QS = pq_qstride(D);
+    constexpr int STAGE_FLOATS = stage_floats(D);
+    constexpr uint32_t STAGE_BYTES = STAGE_FLOATS * sizeof(float);
+    constexpr int NSTAGE = nstage(D);
+    constexpr unsigned FULL = 0xffffffffu;
+    static_assert(TN == 64 && NT == 32, "PQ: one warp per CTA, two tile points per lane");
+
+    const ScoreJob& job = L.jobs[blockIdx.y];
+    const long long M = job.M;
+    const long long qbase = (long long)blockIdx.x * 32;
+    if (qbase >= M || (int)blockIdx.z >= job.nsplit) return;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* stages = reinterpret_cast<float*>(smem_raw);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NSTAGE * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + NSTAGE;
+    u64* rows = reinterpret_cast<u64*>(empty_bar + NSTAGE);           // 32 query rows: {z,z} x D, {-m,-m}
+    float* part = reinterpret_cast<float*>(rows + 32 * QS);           // part[query][lane]
+    unsigned* lmask = reinterpret_cast<unsigned*>(part + 32 * PQ_ROW);   // work list: query mask ...
+    unsigned short* ltile = reinterpret_cast<unsigned short*>(lmask + PQ_CAP);   // ... and tile offset in the chunk
+    __shared__ int s_last[32 / FB];
+
+    const int lane = threadIdx.x;
+    const KdeDev* __restrict__ kde = job.kde;
+    const int ntiles = kde->ntiles;
+    const int nsplit = job.nsplit;
+    const int t0 = (int)(((long long)ntiles * blockIdx.z) / nsplit);
+    const int t1 = (int)(((long long)ntiles * (blockIdx.z + 1)) / nsplit);
+
+    if (lane == 0) {
 #pragma unroll
-        for (int q = 0; q < Q; q++) {
-            const long long v = qbase + (long long)tid * Q + q;          // position in the visit order
-            if (v < M) {
-                const long long r = job.perm ? job.perm[v] : v;          // row of the query table
-                if (myfin.out_m) { myfin.out_m[r] = myfin.log_wmax - (double)mref[q] * LN2; myfin.out_s[r] = S[q]; }
-                if (myfin.out_logp) myfin.out_logp[r] = final_logp(myfin.log_norm, S[q], (double)mref[q]);
+        for (int s = 0; s < NSTAGE; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_fence_init();
+    }
+    __syncwarp();
+
+    u64 q2[Q][D];
+    load_queries<D, Q>(job, kde, qbase, lane, M, q2);
+    float mref[Q], bmin[Q];
+    double S[Q];
+    u64 nm2[Q];
+    mref[0] = 0.f; S[0] = 0.0; nm2[0] = pk(0.f, 0.f);
+    home_reference<D, Q>(kde, ntiles, q2, bmin, mref, nm2);
+
+#pragma unroll
+    for (int k = 0; k < D; k++) rows[lane * QS + k] = q2[0][k];
+    rows[lane * QS + D] = nm2[0];
+    for (int l = 0; l < 32; l++) part[lane * PQ_ROW + l] = 0.f;
+    __syncwarp();
+
+    const float* __restrict__ sbx = kde->sboxes;
+    const float* __restrict__ bx = kde->boxes;
+    const float* __restrict__ gtiles = kde->tiles;
+    const bool cull = job.cull != 0;
+    unsigned n_rerun = 0, n_visited = 0;
+    unsigned long long n_pairs = 0;
+    int epoch_cur = -1;
+    unsigned it = 0;                                   // tiles consumed so far (ring position)
+
+    // request tile `t` into the ring slot of consumption index g (lane 0 only)
+    auto request = [&](unsigned g, int t) {
+        const int sp = (int)(g % NSTAGE);
+        if (g >= (unsigned)NSTAGE) mbar_wait(&empty_bar[sp], ((g / NSTAGE) - 1u) & 1u);
+        mbar_expect_tx(&full_bar[sp], STAGE_BYTES);
+        tma_bulk_g2s(stages + (size_t)sp * STAGE_FLOATS, gtiles + (size_t)t * STAGE_FLOATS, STAGE_BYTES, &full_bar[sp]);
+    };
+
+    const int s_first = t0 / SG, s_end = (t1 + SG - 1) / SG;
+#pragma unroll 1
+    for (int s_base = s_first; s_base < s_end; s_base += PQ_CH) {
+        // ---- (1) super-box tests, one query per lane: lane j keeps the ballot of super-box s_base + j ----
+        unsigned smask = 0u;
+        {
+            float zq[D];
+#pragma unroll
+            for (int k = 0; k < D; k++) { float dup; upk(q2[0][k], zq[k], dup); }
+            const int nsb = s_end - s_base < PQ_CH ? s_end - s_base : PQ_CH;
+#pragma unroll 2
+            for (int j = 0; j < nsb; j++) {
+                const float* b = sbx + (size_t)(s_base + j) * 2 * D;
+                float lb = 0.f;
+                bool valid = true;
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    const float lo = __ldg(b + k), hi = __ldg(b + D + k);
+                    if (k == 0) valid = (lo <= hi);
+                    const float gap = fmaxf(fmaxf(lo - zq[k], zq[k] - hi), 0.f);
+                    lb = fmaf(gap, gap, lb);
+                }
+                const bool need = valid && (!cull || !(lb - mref[0] > CULL_MARGIN));
+                const unsigned bal = __ballot_sync(FULL, need);
+                if (lane == j) smask = bal;
             }
         }
-        return;
-    }
-    // partial states and arrival counters are indexed by visit-order position (shared by a group)
+        // ---- (2) tile tests, one tile per lane (two super-boxes per pass), against the queries of the
+        //          super-box's ballot only; compact the (tile, query mask) pairs into the work list ----
+        int cnt = 0;
+        unsigned act = __ballot_sync(FULL, smask != 0u);
+        while (act) {
+            const int ja = __ffs(act) - 1;
+            act &= act - 1u;
+            int jb = -1;
+            if (act) { jb = __ffs(act) - 1; act &= act - 1u; }
+            const int j = (lane < 16) ? ja : jb;
+            unsigned qm = __shfl_sync(FULL, smask, j < 0 ? 0 : j);
+            const int toff = (j < 0 ? 0 : j) * SG + (lane & 15);
+            const int t = s_base * SG + toff;
+            if (j < 0 || t < t0 || t >= t1) qm = 0u;
+            float lo[D], hi[D];
+            {
+                const int tc = t < ntiles ? t : ntiles - 1;
+                const float* b = bx + (size_t)tc * 2 * D;
+                if (D % 4 == 0) {
 #pragma unroll
-    for (int q = 0; q < Q; q++) {
-        const long long v = qbase + (long long)tid * Q + q;
-        if (v < M) myfin.partial[(long long)blockIdx.z * M + v] = make_double2((double)mref[q], S[q]);
-    }
-    // last-arriving CTA of each finalize block (FB queries) merges splits / forms the ratio + accept
-    __threadfence();
-    __syncthreads();
-    if (tid < QB / FB) {
-        const long long fb = qbase / FB + tid;
-        int last = 0;
-        if (fb * FB < M) {
-            const int prev = atomicAdd(&job.counters[fb], 1);
-            last = (prev == job.expected - 1);
-            if (last) job.counters[fb] = 0;             // self-reset for the next call
+                    for (int k = 0; k < D; k += 4) {
+                        const float4 a = __ldg(reinterpret_cast<const float4*>(b + k));
+                        const float4 c = __ldg(reinterpret_cast<const float4*>(b + D + k));
+                        lo[k] = a.x; lo[k + 1] = a.y; lo[k + 2] = a.z; lo[k + 3] = a.w;
+                        hi[k] = c.x; hi[k + 1] = c.y; hi[k + 2] = c.z; hi[k + 3] = c.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < D; k++) { lo[k] = __ldg(b + k); hi[k] = __ldg(b + D + k); }
+                }
+            }
+            if (!(lo[0] <= hi[0])) qm = 0u;                               // tile without weight
+            unsigned tmask = 0u;
+            while (__any_sync(FULL, qm != 0u)) {
+                const bool on = qm != 0u;
+                const int i = on ? __ffs(qm) - 1 : 0;
+                qm &= qm - 1u;                                            // 0 stays 0
+                const u64* qrow = rows + i * QS;
+                float lb = 0.f;
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    const float zq = reinterpret_cast<const float*>(qrow + k)[0];
+                    const float gap = fmaxf(fmaxf(lo[k] - zq, zq - hi[k]), 0.f);
+                    lb = fmaf(gap, gap, lb);
+                }
+                const float negm = reinterpret_cast<const float*>(qrow + D)[0];
+                if (on && (!cull || !(lb + negm > CULL_MARGIN))) tmask |= 1u << i;
+            }
+            const unsigned nz = __ballot_sync(FULL, tmask != 0u);
+            if (tmask) {
+                const int pos = cnt + __popc(nz & ((1u << lane) - 1u));
+                lmask[pos] = tmask;
+                ltile[pos] = (unsigned short)toff;
+            }
+            cnt += __popc(nz);
         }
-        s_last[tid] = last;
-    }
-    __syncthreads();
+        __syncwarp();
+        if (cnt == 0) continue;
+        n_visited += (unsigned)cnt;
+
+        // ---- (3) stream the work list through the ring ----
+        const int tchunk = s_base * SG;
+        if (lane == 0) {
+            const int npre = cnt < NSTAGE ? cnt : NSTAGE;
+            for (int e = 0; e < npre; e++) request(it + (unsigned)e, tchunk + ltile[e]);
+        }
 #pragma unroll 1
-    for (int b = 0; b < QB / FB; b++) {
-        if (!s_last[b]) continue;
-        __threadfence();
-        for (int i = tid; i < FB; i += NT) {
-            const long long r = qbase + (long long)b * FB + i;
-            if (r < M) finalize_query(L.fin, job.fin_first, job.fin_count, M, r);
+        for (int e = 0; e < cnt; e++, it++) {
+            const int s = (int)(it % NSTAGE);
+            unsigned mask = lmask[e];
+            const int tcur = tchunk + ltile[e];
+            mbar_wait(&full_bar[s], (it / NSTAGE) & 1u);
+            const float* tile = stages + (size_t)s * STAGE_FLOATS;
+
+            const int epoch = tcur >> PQ_EPOCH_SHIFT;
+            if (epoch != epoch_cur) {
+                if (epoch_cur >= 0) { __syncwarp(); S[0] += pq_fold_row(part, lane); __syncwarp(); }
+                epoch_cur = epoch;
+            }
+            // this lane's two points of the tile
+            u64 p2[D];
+#pragma unroll
+            for (int k = 0; k < D; k++) p2[k] = *reinterpret_cast<const u64*>(tile + k * TN + 2 * lane);
+            float w0, w1;
+            upk(*reinterpret_cast<const u64*>(tile + D * TN + 2 * lane), w0, w1);
+            n_pairs += 2u * __popc(mask);
+
+            // rare: a point >= 8 binades closer than the reference was built for (or a NaN row) — fold the
+            // row, move the query's reference to the tile's closest point, re-evaluate
+            auto recentre = [&](int i, float a0, float a1) -> float {
+                float am = fminf(a0, a1);
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) am = fminf(am, __shfl_xor_sync(FULL, am, off));
+                const float delta = floorf(am) - REF_BIAS;
+                n_rerun++;
+                if (delta < 0.f && delta > -1.0e30f) {
+                    __syncwarp();
+                    if (lane == i) {
+                        S[0] += pq_fold_row(part, i);
+                        S[0] = ldexp(S[0], (int)fmaxf(delta, -4000.f));
+                        mref[0] += delta;
+                        nm2[0] = pk(-mref[0], -mref[0]);
+                        rows[i * QS + D] = nm2[0];
+                    }
+                    __syncwarp();
+                    pq_acc<D>(rows + i * QS, p2, a0, a1);
+                    return __fmaf_rn(w1, ex2_neg(a1), __fmul_rn(w0, ex2_neg(a0)));
+                }
+                if (lane == i) S[0] = NAN;                                  // NaN / inf query row: propagate
+                return 0.f;
+            };
+
+            while (mask) {
+                const int i0 = __ffs(mask) - 1;
+                mask &= mask - 1u;
+                if (mask) {
+                    const int i1 = __ffs(mask) - 1;
+                    mask &= mask - 1u;
+                    float a0, a1, b0, b1;
+                    float pa = part[i0 * PQ_ROW + lane];                    // issued early: off the critical path
+                    float pb = part[i1 * PQ_ROW + lane];
+                    pq_acc<D>(rows + i0 * QS, p2, a0, a1);
+                    pq_acc<D>(rows + i1 * QS, p2, b0, b1);
+                    float ta = __fmaf_rn(w1, ex2_neg(a1), __fmul_rn(w0, ex2_neg(a0)));
+                    float tb = __fmaf_rn(w1, ex2_neg(b1), __fmul_rn(w0, ex2_neg(b0)));
+                    if (__any_sync(FULL, !(ta < PQ_LIMIT) || !(tb < PQ_LIMIT))) {
+                        if (__any_sync(FULL, !(ta < PQ_LIMIT))) { ta = recentre(i0, a0, a1); pa = part[i0 * PQ_ROW + lane]; }
+                        if (__any_sync(FULL, !(tb < PQ_LIMIT))) { tb = recentre(i1, b0, b1); pb = part[i1 * PQ_ROW + lane]; }
+                    }
+                    part[i0 * PQ_ROW + lane] = pa + ta;
+                    part[i1 * PQ_ROW + lane] = pb + tb;
+                } else {
+                    float a0, a1;
+                    float pa = part[i0 * PQ_ROW + lane];
+                    pq_acc<D>(rows + i0 * QS, p2, a0, a1);
+                    float ta = __fmaf_rn(w1, ex2_neg(a1), __fmul_rn(w0, ex2_neg(a0)));
+                    if (__any_sync(FULL, !(ta < PQ_LIMIT))) { ta = recentre(i0, a0, a1); pa = part[i0 * PQ_ROW + lane]; }
+                    part[i0 * PQ_ROW + lane] = pa + ta;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&empty_bar[s]);
+                if (e + NSTAGE < cnt) request(it + (unsigned)NSTAGE, tchunk + ltile[e + NSTAGE]);
+            }
         }
+        __syncwarp();                                                      // the list is rebuilt next chunk
     }
+    __syncwarp();
+    S[0] += pq_fold_row(part, lane);
+
+    if (lane == 0) {
+        if (n_rerun) atomicAdd(&g_stats[0], (unsigned long long)n_rerun * 2);
+        atomicAdd(&g_stats[1], n_pairs);
+        atomicAdd(&g_stats[2], (unsigned long long)((unsigned)(t1 - t0) - n_visited));
+        atomicAdd(&g_stats[3], (unsigned long long)(t1 - t0));
+    }
+    finish_queries<D, Q>(L, job, qbase, lane, M, mref, S, s_last);
 }
 
 template <int D, int Q>
 static cudaError_t launch_score_dq(const ScoreLaunch& L, int njobs, long long max_qblocks, int max_split,
                                    int max_ntiles, cudaStream_t st)
 {
-    constexpr int NSTAGE = nstage(D);
-    const size_t smem = (size_t)NSTAGE * stage_floats(D) * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t) +
-                        pq_smem_bytes(D, Q) + (((size_t)max_ntiles + 31) / 32) * 4 + 16;
-    cudaError_t e = cudaFuncSetAttribute(skb_score_kernel<D, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     dim3 grid((unsigned)max_qblocks, (unsigned)njobs, (unsigned)max_split);
-    skb_score_kernel<D, Q><<<grid, NT, smem, st>>>(L);
+    if constexpr (pq_mode(D, Q)) {
+        const size_t smem = pq_smem_bytes(D);
+        cudaError_t e = cudaFuncSetAttribute(skb_score_pq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        skb_score_pq_kernel<D><<<grid, 32, smem, st>>>(L);
+    } else {
+        constexpr int NSTAGE = nstage(D);
+        const size_t smem = (size_t)NSTAGE * stage_floats(D) * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t) +
+                            (((size_t)max_ntiles + 31) / 32) * 4 + 16;
+        cudaError_t e = cudaFuncSetAttribute(skb_score_kernel<D, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        skb_score_kernel<D, Q><<<grid, NT, smem, st>>>(L);
+    }
     count_launch();
     return cudaGetLastError();
 }
@@ -1034,12 +1229,19 @@ cudaError_t read_stats(unsigned long long* out4, int reset)
 template <int D, int Q>
 static int occupancy_dq()
 {
-    constexpr int NSTAGE = nstage(D);
-    const size_t smem = (size_t)NSTAGE * stage_floats(D) * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t) +
-                        pq_smem_bytes(D, Q) + 1024;
     int n = 0;
-    if (cudaFuncSetAttribute(skb_score_kernel<D, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, skb_score_kernel<D, Q>, NT, smem) != cudaSuccess) {
+    cudaError_t e;
+    if constexpr (pq_mode(D, Q)) {
+        const size_t smem = pq_smem_bytes(D);
+        e = cudaFuncSetAttribute(skb_score_pq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, skb_score_pq_kernel<D>, 32, smem);
+    } else {
+        constexpr int NSTAGE = nstage(D);
+        const size_t smem = (size_t)NSTAGE * stage_floats(D) * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t) + 1024;
+        e = cudaFuncSetAttribute(skb_score_kernel<D, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, skb_score_kernel<D, Q>, NT, smem);
+    }
+    if (e != cudaSuccess) {
         cudaGetLastError();
         return 2;
     }
