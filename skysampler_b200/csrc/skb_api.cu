@@ -116,9 +116,10 @@ static void kd_order(const float* z, int D, int* idx, long long n)
     }
     int kbest = 0;
     for (int k = 1; k < D; k++) if (hi[k] - lo[k] > hi[kbest] - lo[kbest]) kbest = k;
-    // split in whole super-boxes (SG tiles) while the node is larger than one, then in whole tiles: every
-    // aligned run of SG tiles is then a kd subtree, so its union box is as tight as the tree allows
-    const long long unit = n > (long long)SG * TN ? (long long)SG * TN : TN;
+    // split in whole chunks (CG super-boxes) while the node is larger than one, then in whole super-boxes (SG
+    // tiles), then in whole tiles: every aligned run of SG tiles / CG super-boxes is then a kd subtree, so
+    // its union box is as tight as the tree allows
+    const long long unit = n > (long long)CG * SG * TN ? (long long)CG * SG * TN : (n > (long long)SG * TN ? (long long)SG * TN : TN);
     const long long nunit = (n + unit - 1) / unit;
     const long long nl = ((nunit + 1) / 2) * unit;        // 0 < nl < n because nunit >= 2
     std::nth_element(idx, idx + nl, idx + n,
@@ -485,11 +486,14 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
     SKB_CUDA_C(cudaMalloc(&k->tiles, tile_bytes));
     SKB_CUDA_C(cudaMalloc(&k->boxes, (size_t)hk.ntiles * 2 * d * sizeof(float)));
     hk.nsuper = (hk.ntiles + SG - 1) / SG;
-    SKB_CUDA_C(cudaMalloc(&k->sboxes, (size_t)hk.nsuper * 2 * d * sizeof(float)));
-    SKB_CUDA_C(launch_pack(k->zt64, k->perm, d, hk.c, d_w, 1.0 / wmax, k->tiles, hk.ntiles, k->boxes, k->sboxes, 0));
+    hk.nchunk = (hk.nsuper + CG - 1) / CG;
+    SKB_CUDA_C(cudaMalloc(&k->sboxes, (size_t)(hk.nsuper + hk.nchunk) * 2 * d * sizeof(float)));   // super-boxes, then chunk boxes
+    float* cboxes = k->sboxes + (size_t)hk.nsuper * 2 * d;
+    SKB_CUDA_C(launch_pack(k->zt64, k->perm, d, hk.c, d_w, 1.0 / wmax, k->tiles, hk.ntiles, k->boxes, k->sboxes, cboxes, 0));
     hk.tiles = k->tiles;
     hk.boxes = k->boxes;
     hk.sboxes = k->sboxes;
+    hk.cboxes = cboxes;
     SKB_CUDA_C(cudaMemcpy(k->dk, &hk, sizeof(KdeDev), cudaMemcpyHostToDevice));
     SKB_CUDA_C(cudaStreamSynchronize(0));
     cudaFree(k->perm);

@@ -87,19 +87,19 @@ __global__ void skb_box_kernel(float* __restrict__ tiles, const int* __restrict_
     }
 }
 
-// union boxes of SG consecutive tiles: one thread per (super-box, coordinate)
-__global__ void skb_superbox_kernel(const float* __restrict__ boxes, int D, int ntiles, int nsuper, float* __restrict__ sboxes)
+// union boxes of `group` consecutive boxes: one thread per (output box, coordinate)
+__global__ void skb_groupbox_kernel(const float* __restrict__ boxes, int D, int nin, int group, int nout, float* __restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nsuper * D) return;
+    if (i >= nout * D) return;
     const int s = i / D, k = i % D;
     float lo = INFINITY, hi = -INFINITY;
-    for (int t = s * SG; t < ntiles && t < (s + 1) * SG; t++) {
+    for (int t = s * group; t < nin && t < (s + 1) * group; t++) {
         const float a = boxes[(size_t)t * 2 * D + k], b = boxes[(size_t)t * 2 * D + D + k];
         if (a <= b) { lo = fminf(lo, a); hi = fmaxf(hi, b); }
     }
-    sboxes[(size_t)s * 2 * D + k] = lo;
-    sboxes[(size_t)s * 2 * D + D + k] = hi;
+    out[(size_t)s * 2 * D + k] = lo;
+    out[(size_t)s * 2 * D + D + k] = hi;
 }
 
 cudaError_t launch_fit(const void* train, int f32, long long N, int D, long long ld, int is_whitened,
@@ -112,15 +112,17 @@ cudaError_t launch_fit(const void* train, int f32, long long N, int D, long long
 }
 
 cudaError_t launch_pack(const double* zt64, const int* perm, int D, double c, const double* w, double inv_wmax,
-                        float* tiles, int ntiles, float* boxes, float* sboxes, cudaStream_t st)
+                        float* tiles, int ntiles, float* boxes, float* sboxes, float* cboxes, cudaStream_t st)
 {
     const long long total = (long long)ntiles * tile_points(D);
     const int bs = 256;
     skb_pack_kernel<<<(unsigned)((total + bs - 1) / bs), bs, 0, st>>>(zt64, perm, D, c, w, inv_wmax, tiles, ntiles);
     skb_box_kernel<<<(unsigned)((ntiles + 7) / 8), 256, 0, st>>>(tiles, perm, D, ntiles, boxes);
     const int nsuper = (ntiles + SG - 1) / SG;
-    skb_superbox_kernel<<<(unsigned)((nsuper * D + 127) / 128), 128, 0, st>>>(boxes, D, ntiles, nsuper, sboxes);
-    count_launch(3);
+    skb_groupbox_kernel<<<(unsigned)((nsuper * D + 127) / 128), 128, 0, st>>>(boxes, D, ntiles, SG, nsuper, sboxes);
+    const int nchunk = (nsuper + CG - 1) / CG;
+    skb_groupbox_kernel<<<(unsigned)((nchunk * D + 127) / 128), 128, 0, st>>>(sboxes, D, nsuper, CG, nchunk, cboxes);
+    count_launch(4);
     return cudaGetLastError();
 }
 

@@ -46,6 +46,10 @@ constexpr int FB = 32;               // queries per finalize block (arrival-coun
 #define SKB_SG 16
 #endif
 constexpr int SG = SKB_SG;               // tiles per super-box (consecutive kd leaves = one kd subtree)
+#ifndef SKB_CG
+#define SKB_CG 16
+#endif
+constexpr int CG = SKB_CG;               // super-boxes per chunk box (third level of the box hierarchy)
 constexpr float PAD_COORD = 1.0e18f; // coordinate of padding / zero-weight points: exp2(-1e36) == 0
 
 #ifndef SKB_Q_LE2
@@ -83,9 +87,11 @@ struct KdeDev {
     const double* cumsum_w;  // [N] sequential fp64 cumsum (NULL for unweighted)
     const float* boxes;      // [ntiles][2][D] lo / hi of the packed fp32 coordinates
     const float* sboxes;     // [nsuper][2][D] union boxes of SG consecutive tiles
+    const float* cboxes;     // [nchunk][2][D] union boxes of CG consecutive super-boxes
     long long N;
     int ntiles;
     int nsuper;
+    int nchunk;
     int D;
     int has_w;
     int has_winv;
@@ -152,7 +158,7 @@ struct ScoreLaunch {
 cudaError_t launch_fit(const void* train, int f32, long long N, int D, long long ld, int is_whitened,
                        const KdeDev* kde_dev, double* zt64, cudaStream_t st);
 cudaError_t launch_pack(const double* zt64, const int* perm, int D, double c, const double* w, double inv_wmax,
-                        float* tiles, int ntiles, float* boxes, float* sboxes, cudaStream_t st);
+                        float* tiles, int ntiles, float* boxes, float* sboxes, float* cboxes, cudaStream_t st);
 size_t sort_temp_bytes(long long M);
 cudaError_t launch_query_order(const KdeDev* kde, const void* q, int q_f32, long long M, long long ldq,
                                int q_is_whitened, const signed char* cols_dev, unsigned long long* keys_in,

@@ -105,6 +105,9 @@ constexpr float CULL_MARGIN = 128.f;              // box lower bound this far pa
 #ifndef SKB_STEP8
 #define SKB_STEP8 1       // 1: 8 training points per inner step when a thread holds <= 2 queries
 #endif
+#ifndef SKB_HOME_SUPER
+#define SKB_HOME_SUPER 1   // 1: for D >= 5 the exponent reference comes from an exact scan of the whole home super-box
+#endif
 #ifndef SKB_PREFETCH
 #define SKB_PREFETCH 0     // 1: double-buffer the tile words of the next 4 points in registers
 #endif
@@ -452,22 +455,49 @@ __device__ __forceinline__ void home_reference(const KdeDev* __restrict__ kde, i
         int sbest[Q];
 #pragma unroll
         for (int q = 0; q < Q; q++) { lbbest[q] = INFINITY; sbest[q] = 0; }
+        // branch and bound over the chunk boxes: a chunk whose box is no closer than the best super-box so
+        // far cannot hold a closer one (ties keep the first), so the warp skips it when no lane wants it
+        const float* __restrict__ cbx = kde->cboxes;
+        const int nchunk = kde->nchunk;
 #pragma unroll 1
-        for (int sidx = 0; sidx < nsuper; sidx++) {
-            float lo[D], hi[D];
+        for (int cidx = 0; cidx < nchunk; cidx++) {
+            bool want = false;
+            {
+                float lo[D], hi[D];
 #pragma unroll
-            for (int k = 0; k < D; k++) { lo[k] = __ldg(sbx + (size_t)sidx * 2 * D + k); hi[k] = __ldg(sbx + (size_t)sidx * 2 * D + D + k); }
-            if (!(lo[0] <= hi[0])) continue;
+                for (int k = 0; k < D; k++) { lo[k] = __ldg(cbx + (size_t)cidx * 2 * D + k); hi[k] = __ldg(cbx + (size_t)cidx * 2 * D + D + k); }
 #pragma unroll
-            for (int q = 0; q < Q; q++) {
-                float lb = 0.f;
+                for (int q = 0; q < Q; q++) {
+                    float lb = 0.f;
 #pragma unroll
-                for (int k = 0; k < D; k++) {
-                    float zq, dup; upk(q2[q][k], zq, dup);
-                    const float gap = fmaxf(fmaxf(lo[k] - zq, zq - hi[k]), 0.f);
-                    lb = fmaf(gap, gap, lb);
+                    for (int k = 0; k < D; k++) {
+                        float zq, dup; upk(q2[q][k], zq, dup);
+                        const float gap = fmaxf(fmaxf(lo[k] - zq, zq - hi[k]), 0.f);
+                        lb = fmaf(gap, gap, lb);
+                    }
+                    want |= (lb < lbbest[q]);
                 }
-                if (lb < lbbest[q]) { lbbest[q] = lb; sbest[q] = sidx; }
+                if (!(lo[0] <= hi[0])) want = false;
+            }
+            if (!__any_sync(0xffffffffu, want)) continue;
+            const int send = (cidx + 1) * CG < nsuper ? (cidx + 1) * CG : nsuper;
+#pragma unroll 1
+            for (int sidx = cidx * CG; sidx < send; sidx++) {
+                float lo[D], hi[D];
+#pragma unroll
+                for (int k = 0; k < D; k++) { lo[k] = __ldg(sbx + (size_t)sidx * 2 * D + k); hi[k] = __ldg(sbx + (size_t)sidx * 2 * D + D + k); }
+                if (!(lo[0] <= hi[0])) continue;
+#pragma unroll
+                for (int q = 0; q < Q; q++) {
+                    float lb = 0.f;
+#pragma unroll
+                    for (int k = 0; k < D; k++) {
+                        float zq, dup; upk(q2[q][k], zq, dup);
+                        const float gap = fmaxf(fmaxf(lo[k] - zq, zq - hi[k]), 0.f);
+                        lb = fmaf(gap, gap, lb);
+                    }
+                    if (lb < lbbest[q]) { lbbest[q] = lb; sbest[q] = sidx; }
+                }
             }
         }
 #pragma unroll
@@ -504,6 +534,32 @@ __device__ __forceinline__ void home_reference(const KdeDev* __restrict__ kde, i
                     a0 = fmaf(d0, d0, a0); a1 = fmaf(d1, d1, a1); a2 = fmaf(d2, d2, a2); a3 = fmaf(d3, d3, a3);
                 }
                 best = fminf(best, fminf(fminf(a0, a1), fminf(a2, a3)));
+            }
+            // D >= 5: the other tiles of the home super-box whose box is closer than the best point so far
+#pragma unroll 1
+            for (int t = sbest[q] * SG; SKB_HOME_SUPER && D >= 5 && t < tend; t++) {
+                float lb = 0.f;
+                bool valid = (t != tbest);
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    const float lo = __ldg(bx + (size_t)t * 2 * D + k), hi = __ldg(bx + (size_t)t * 2 * D + D + k);
+                    valid &= (lo <= hi);
+                    const float gap = fmaxf(fmaxf(lo - zq[k], zq[k] - hi), 0.f);
+                    lb = fmaf(gap, gap, lb);
+                }
+                if (!(valid && lb < best)) continue;
+                const float* __restrict__ ot = kde->tiles + (size_t)t * STAGE_FLOATS;
+#pragma unroll 1
+                for (int j = 0; j < TN; j += 4) {
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                    for (int k = 0; k < D; k++) {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(ot + k * TN + j));
+                        const float d0 = zq[k] - v.x, d1 = zq[k] - v.y, d2 = zq[k] - v.z, d3 = zq[k] - v.w;
+                        a0 = fmaf(d0, d0, a0); a1 = fmaf(d1, d1, a1); a2 = fmaf(d2, d2, a2); a3 = fmaf(d3, d3, a3);
+                    }
+                    best = fminf(best, fminf(fminf(a0, a1), fminf(a2, a3)));
+                }
             }
             if (!(best < 1.0e30f)) best = REF_BIAS;                   // inf/NaN rows (or padding only): finite reference
             bmin[q] = best;
@@ -590,7 +646,7 @@ __device__ __forceinline__ void finish_queries(const ScoreLaunch& L, const Score
 #define SKB_TEST_UNROLL 4     // tile box tests of the need-bitmap phase (lanes = queries kernel) in flight at once
 #endif
 #ifndef SKB_PQ_MIN_D
-#define SKB_PQ_MIN_D 6
+#define SKB_PQ_MIN_D 5
 #endif
 #ifndef SKB_PQ_MINB
 #define SKB_PQ_MINB 16        // launch bound (CTAs per SM) of the PQ kernel for D <= 8
@@ -598,21 +654,21 @@ __device__ __forceinline__ void finish_queries(const ScoreLaunch& L, const Score
 #ifndef SKB_PQ_MINB_HI
 #define SKB_PQ_MINB_HI 16     // same for D > 8
 #endif
-#ifndef SKB_PQ_CH
-#define SKB_PQ_CH 16          // super-boxes per chunk (<= 32)
-#endif
-constexpr int PQ_CH = SKB_PQ_CH;
+constexpr int PQ_CH = CG;                         // one work list per chunk box
 constexpr int PQ_CAP = PQ_CH * SG;                // work-list capacity: every tile of a chunk
 constexpr int PQ_EPOCH_SHIFT = 7;                 // fp32 row partials are folded into fp64 every 128 tile indices
 constexpr int PQ_ROW = 33;                        // row stride of part[][] (floats): conflict-free row walks
-constexpr float PQ_LIMIT = 2.0679515e-25f;        // 2^-82 = 2^(8 - REF_BIAS): a point >= 8 binades closer than the reference
-static_assert(PQ_CH <= 32 && PQ_CAP <= 65536 && SG == 16, "PQ chunk layout");
+#ifndef SKB_PQ_SLACK
+#define SKB_PQ_SLACK 3        // a lane term >= 2^(SLACK - REF_BIAS) (a point that much closer than the reference) recentres
+#endif
+constexpr float PQ_LIMIT = 8.0779357e-28f * (float)(1u << SKB_PQ_SLACK);   // 2^(SLACK - 90)
+static_assert(PQ_CH <= 32 && PQ_CAP <= 256 && SG == 16, "PQ chunk layout");
 __host__ __device__ constexpr bool pq_mode(int D, int Q) { return SKB_PQ && D >= SKB_PQ_MIN_D && Q == 1 && tile_points(D) == 64; }
 __host__ __device__ constexpr int pq_qstride(int D) { return (D + 2) & ~1; }          // u64 words per query row ({z,z} x D, {-m,-m})
 __host__ __device__ constexpr size_t pq_smem_bytes(int D)
 {
     return (size_t)nstage(D) * stage_floats(D) * 4 + (size_t)nstage(D) * 16 + (size_t)32 * pq_qstride(D) * 8 +
-           (size_t)32 * PQ_ROW * 4 + (size_t)PQ_CAP * 4 + (size_t)PQ_CAP * 2 + 16;
+           (size_t)32 * PQ_ROW * 4 + (size_t)PQ_CAP * 4 + (size_t)PQ_CAP + 16;
 }
 
 // acc - m for this lane's two points against the query row in shared memory
@@ -959,7 +1015,7 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
     u64* rows = reinterpret_cast<u64*>(empty_bar + NSTAGE);           // 32 query rows: {z,z} x D, {-m,-m}
     float* part = reinterpret_cast<float*>(rows + 32 * QS);           // part[query][lane]
     unsigned* lmask = reinterpret_cast<unsigned*>(part + 32 * PQ_ROW);   // work list: query mask ...
-    unsigned short* ltile = reinterpret_cast<unsigned short*>(lmask + PQ_CAP);   // ... and tile offset in the chunk
+    unsigned char* ltile = reinterpret_cast<unsigned char*>(lmask + PQ_CAP);   // ... and tile offset in the chunk
     __shared__ int s_last[32 / FB];
 
     const int lane = threadIdx.x;
@@ -990,6 +1046,7 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
     for (int l = 0; l < 32; l++) part[lane * PQ_ROW + l] = 0.f;
     __syncwarp();
 
+    const float* __restrict__ cbx = kde->cboxes;
     const float* __restrict__ sbx = kde->sboxes;
     const float* __restrict__ bx = kde->boxes;
     const float* __restrict__ gtiles = kde->tiles;
@@ -1007,15 +1064,27 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
         tma_bulk_g2s(stages + (size_t)sp * STAGE_FLOATS, gtiles + (size_t)t * STAGE_FLOATS, STAGE_BYTES, &full_bar[sp]);
     };
 
-    const int s_first = t0 / SG, s_end = (t1 + SG - 1) / SG;
+    const int s_first = (t0 / SG / PQ_CH) * PQ_CH, s_end = (t1 + SG - 1) / SG;   // chunk aligned; tiles outside [t0, t1) are masked
 #pragma unroll 1
     for (int s_base = s_first; s_base < s_end; s_base += PQ_CH) {
-        // ---- (1) super-box tests, one query per lane: lane j keeps the ballot of super-box s_base + j ----
+        // ---- (1) chunk-box test, then super-box tests, one query per lane: lane j keeps the ballot of
+        //          super-box s_base + j ----
         unsigned smask = 0u;
         {
             float zq[D];
 #pragma unroll
             for (int k = 0; k < D; k++) { float dup; upk(q2[0][k], zq[k], dup); }
+            if (cull) {
+                const float* b = cbx + (size_t)(s_base / PQ_CH) * 2 * D;
+                float lb = 0.f;
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    const float lo = __ldg(b + k), hi = __ldg(b + D + k);
+                    const float gap = fmaxf(fmaxf(lo - zq[k], zq[k] - hi), 0.f);
+                    lb = fmaf(gap, gap, lb);
+                }
+                if (!__any_sync(FULL, !(lb - mref[0] > CULL_MARGIN))) continue;
+            }
             const int nsb = s_end - s_base < PQ_CH ? s_end - s_base : PQ_CH;
 #pragma unroll 2
             for (int j = 0; j < nsb; j++) {
@@ -1086,7 +1155,7 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
             if (tmask) {
                 const int pos = cnt + __popc(nz & ((1u << lane) - 1u));
                 lmask[pos] = tmask;
-                ltile[pos] = (unsigned short)toff;
+                ltile[pos] = (unsigned char)toff;
             }
             cnt += __popc(nz);
         }
