@@ -381,7 +381,7 @@ def run_ours(args):
         os.environ.pop("SKB_NO_CULL", None)
         lib.skb_debug_counters(local, (C.c_uint64 * 4)(), 1)
 
-    # ---- roofline of the dominant kernel (skb_score_kernel<8,4>), peaks measured live on this GPU ----
+    # ---- roofline of the dominant kernel (skb_score_pq_kernel<8>), peaks measured live on this GPU ----
     roof = None
     if rank == 0:
         fma, ex2 = C.c_double(), C.c_double()
@@ -405,7 +405,7 @@ def run_ours(args):
         dense_rate = pairs_per_step_rank / (dense_ms * 1e-3)
         roof = {
             # bound: the FP32 FMA pipe (with the SFU as second limit) — not HBM, not tensor cores
-            "bound": "fp32", "kernel": "skb::skb_score_kernel<8,1>",
+            "bound": "fp32", "kernel": "skb::skb_score_pq_kernel<8>",
             "achieved": ach * flop_pair / 1e12, "peak": peak_pairs * flop_pair / 1e12, "unit": "TFLOP/s",
             "frac": ach / peak_pairs, "traffic": traffic,
             "definition": "achieved = ALGORITHMIC work: pairs/launch x (3d+1) FP32 FLOP / CUDA-event launch time, "

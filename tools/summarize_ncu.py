@@ -56,8 +56,8 @@ if rep != "-":
     print("dram read %.1f MB write %.1f MB  duration %s %s" % (rd / 1e6, wr / 1e6, d["gpu__time_duration.sum"], u["gpu__time_duration.sum"]))
     if name == "score_d8_bench":
         json.dump({"batch": 1 << 20, "ntrain": 1000000, "dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
-                   "source": "profiles/%s_%s_ncu_full.txt (ncu --set full, one launch of skb_score_kernel<8>)" % (tag, name),
-                   "algorithmic_bytes_per_launch": (1 << 20) * (8 * 8 + 8 + 1 + 1) + 2 * 3907 * 9 * 256 * 4},
+                   "source": "profiles/%s_%s_ncu_full.txt (ncu --set full, one launch of skb_score_pq_kernel<8>)" % (tag, name),
+                   "algorithmic_bytes_per_launch": (1 << 20) * (8 * 8 + 8 + 1 + 1) + 2 * 15625 * 10 * 64 * 4},
                   open(os.path.join(PROF, "roofline_traffic.json"), "w"), indent=1)
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(src.splitlines()))
