@@ -77,7 +77,10 @@ __host__ __device__ constexpr int queries_per_thread(int D)
 // Second instantiation, tuned for the all-pairs evaluation (culling off, SKB_NO_CULL=1): more queries per
 // thread = more independent FMA chains and fewer LDS per pair.  A query's arithmetic does not depend on Q
 // (each query is a private register chain), so both variants give bit-identical results.
-__host__ __device__ constexpr int queries_per_thread_dense(int D) { return D <= 4 ? 8 : (D <= 8 ? 4 : 2); }
+#ifndef SKB_DENSE_QMUL
+#define SKB_DENSE_QMUL 1
+#endif
+__host__ __device__ constexpr int queries_per_thread_dense(int D) { return (D <= 4 ? 8 : (D <= 8 ? 4 : 2)) * SKB_DENSE_QMUL; }
 __host__ __device__ constexpr int stage_floats(int D) { return (D + 2) * tile_points(D); }   // D coords, weights, header (box)
 
 // Device-resident description of one fitted KDE (one per handle, uploaded at skb_create).

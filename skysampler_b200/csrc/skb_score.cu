@@ -26,6 +26,7 @@
 // (LDS.128 broadcast), each thread owning Q whole queries, so no cross-lane reduction exists.
 #include "skb_internal.h"
 #include <math.h>
+#include <type_traits>
 
 namespace skb {
 
@@ -186,17 +187,19 @@ __device__ __forceinline__ void exp2_neg_poly2_batch(u64 (&v)[Q])
 }
 
 template <int D, int Q, bool MIN_ONLY, bool POLY_B = false>
-__device__ __forceinline__ void step_compute(const StepOperands<D>& op, const u64 (&q2)[Q][D], const u64 (&nm2)[Q],
+__device__ __forceinline__ void step_compute(const StepOperands<D>& op, const float (&q2)[Q][D], const float (&nm2)[Q],
                                              u64 (&sum2)[Q], float (&amin)[Q])
 {
     u64 pb[Q];
 #pragma unroll
     for (int q = 0; q < Q; q++) {
-        u64 aa = nm2[q], ab = nm2[q];
+        const u64 seed = pk(nm2[q], nm2[q]);
+        u64 aa = seed, ab = seed;
 #pragma unroll
         for (int k = 0; k < D; k++) {
-            const u64 da = sub2(q2[q][k], op.xa[k]);
-            const u64 db = sub2(q2[q][k], op.xb[k]);
+            const u64 qk = pk(q2[q][k], q2[q][k]);     // folds into the scalar-broadcast operand form (R.F32)
+            const u64 da = sub2(qk, op.xa[k]);
+            const u64 db = sub2(qk, op.xb[k]);
             aa = fma2(da, da, aa);
             ab = fma2(db, db, ab);
         }
@@ -227,8 +230,8 @@ __device__ __forceinline__ void step_compute(const StepOperands<D>& op, const u6
 // 8 points per step (four packed pairs per dimension): with Q <= 2 queries per thread a 4-point step has
 // only 2Q independent FMA chains in flight, too few to cover the FFMA2 latency; this doubles them.
 template <int D, int Q, bool MIN_ONLY>
-__device__ __forceinline__ void step_compute8(const float* __restrict__ tile, int j, const u64 (&q2)[Q][D],
-                                              const u64 (&nm2)[Q], u64 (&sum2)[Q], float (&amin)[Q])
+__device__ __forceinline__ void step_compute8(const float* __restrict__ tile, int j, const float (&q2)[Q][D],
+                                              const float (&nm2)[Q], u64 (&sum2)[Q], float (&amin)[Q])
 {
     constexpr int TN = tile_points(D);
     u64 xa[D], xb[D], xc[D], xd[D];
@@ -246,13 +249,15 @@ __device__ __forceinline__ void step_compute8(const float* __restrict__ tile, in
     }
 #pragma unroll
     for (int q = 0; q < Q; q++) {
-        u64 aa = nm2[q], ab = nm2[q], ac = nm2[q], ad = nm2[q];
+        const u64 seed = pk(nm2[q], nm2[q]);
+        u64 aa = seed, ab = seed, ac = seed, ad = seed;
 #pragma unroll
         for (int k = 0; k < D; k++) {
-            const u64 da = sub2(q2[q][k], xa[k]);
-            const u64 db = sub2(q2[q][k], xb[k]);
-            const u64 dc = sub2(q2[q][k], xc[k]);
-            const u64 dd = sub2(q2[q][k], xd[k]);
+            const u64 qk = pk(q2[q][k], q2[q][k]);
+            const u64 da = sub2(qk, xa[k]);
+            const u64 db = sub2(qk, xb[k]);
+            const u64 dc = sub2(qk, xc[k]);
+            const u64 dd = sub2(qk, xd[k]);
             aa = fma2(da, da, aa);
             ab = fma2(db, db, ab);
             ac = fma2(dc, dc, ac);
@@ -278,7 +283,7 @@ __device__ __forceinline__ void step_compute8(const float* __restrict__ tile, in
 // npts must be a multiple of 8.
 template <int D, int Q, bool MIN_ONLY>
 __device__ __forceinline__ void tile_pass(const float* __restrict__ tile, int npts,
-                                          const u64 (&q2)[Q][D], const u64 (&nm2)[Q],
+                                          const float (&q2)[Q][D], const float (&nm2)[Q],
                                           u64 (&sum2)[Q], float (&amin)[Q])
 {
 #if SKB_PREFETCH
@@ -380,7 +385,7 @@ __device__ __forceinline__ void finalize_query(const FinTable& fin, int first, i
 // ---- load this thread's Q query rows, whiten + prescale in fp64, pack as {z, z} ----
 template <int D, int Q>
 __device__ __forceinline__ void load_queries(const ScoreJob& job, const KdeDev* __restrict__ kde, long long qbase, int tid,
-                                             long long M, u64 (&q2)[Q][D])
+                                             long long M, float (&q2)[Q][D])
 {
     {
         const double c = kde->c;
@@ -417,7 +422,7 @@ __device__ __forceinline__ void load_queries(const ScoreJob& job, const KdeDev* 
             }
             if (job.q_is_whitened) {
 #pragma unroll
-                for (int k = 0; k < D; k++) { const float z = (float)(x[k] * c); q2[q][k] = pk(z, z); }
+                for (int k = 0; k < D; k++) q2[q][k] = (float)(x[k] * c);
             } else {
 #pragma unroll
                 for (int i = 0; i < D; i++) x[i] -= kde->mu[i];
@@ -426,8 +431,7 @@ __device__ __forceinline__ void load_queries(const ScoreJob& job, const KdeDev* 
                     double z = 0.0;
 #pragma unroll
                     for (int i = 0; i < D; i++) z = fma(x[i], kde->Wc[i * D + k], z);
-                    const float zf = (float)z;
-                    q2[q][k] = pk(zf, zf);
+                    q2[q][k] = (float)z;
                 }
             }
         }
@@ -442,8 +446,8 @@ __device__ __forceinline__ void load_queries(const ScoreJob& job, const KdeDev* 
 //      so the reference is tight from the first tile on — tight references are what lets the box test
 //      cull.  (If a closer point turns up later the reference is tightened / recentred on the fly.)
 template <int D, int Q>
-__device__ __forceinline__ void home_reference(const KdeDev* __restrict__ kde, int ntiles, const u64 (&q2)[Q][D],
-                                               float (&bmin)[Q], float (&mref)[Q], u64 (&nm2)[Q])
+__device__ __forceinline__ void home_reference(const KdeDev* __restrict__ kde, int ntiles, const float (&q2)[Q][D],
+                                               float (&bmin)[Q], float (&mref)[Q], float (&nm2)[Q])
 {
     constexpr int TN = tile_points(D);
     constexpr int STAGE_FLOATS = stage_floats(D);
@@ -471,7 +475,7 @@ __device__ __forceinline__ void home_reference(const KdeDev* __restrict__ kde, i
                     float lb = 0.f;
 #pragma unroll
                     for (int k = 0; k < D; k++) {
-                        float zq, dup; upk(q2[q][k], zq, dup);
+                        const float zq = q2[q][k];
                         const float gap = fmaxf(fmaxf(lo[k] - zq, zq - hi[k]), 0.f);
                         lb = fmaf(gap, gap, lb);
                     }
@@ -492,7 +496,7 @@ __device__ __forceinline__ void home_reference(const KdeDev* __restrict__ kde, i
                     float lb = 0.f;
 #pragma unroll
                     for (int k = 0; k < D; k++) {
-                        float zq, dup; upk(q2[q][k], zq, dup);
+                        const float zq = q2[q][k];
                         const float gap = fmaxf(fmaxf(lo[k] - zq, zq - hi[k]), 0.f);
                         lb = fmaf(gap, gap, lb);
                     }
@@ -504,7 +508,7 @@ __device__ __forceinline__ void home_reference(const KdeDev* __restrict__ kde, i
         for (int q = 0; q < Q; q++) {
             float zq[D];
 #pragma unroll
-            for (int k = 0; k < D; k++) { float dup; upk(q2[q][k], zq[k], dup); }
+            for (int k = 0; k < D; k++) zq[k] = q2[q][k];
             // nearest tile box inside the home super-box
             int tbest = sbest[q] * SG;
             float lbt = INFINITY;
@@ -565,7 +569,7 @@ __device__ __forceinline__ void home_reference(const KdeDev* __restrict__ kde, i
             bmin[q] = best;
             const float m = floorf(best) - REF_BIAS;
             mref[q] = m;
-            nm2[q] = pk(-m, -m);
+            nm2[q] = -m;
         }
     }
 }
@@ -657,49 +661,54 @@ __device__ __forceinline__ void finish_queries(const ScoreLaunch& L, const Score
 constexpr int PQ_CH = CG;                         // one work list per chunk box
 constexpr int PQ_CAP = PQ_CH * SG;                // work-list capacity: every tile of a chunk
 constexpr int PQ_EPOCH_SHIFT = 7;                 // fp32 row partials are folded into fp64 every 128 tile indices
-constexpr int PQ_ROW = 33;                        // row stride of part[][] (floats): conflict-free row walks
+constexpr int PQ_ROW = 32;                        // part[query][lane ^ query]: conflict-free for both walks
+#ifndef SKB_PQ_UNROLL
+#define SKB_PQ_UNROLL 2       // queries of a tile's mask evaluated per step (2 or 4)
+#endif
 #ifndef SKB_PQ_SLACK
 #define SKB_PQ_SLACK 3        // a lane term >= 2^(SLACK - REF_BIAS) (a point that much closer than the reference) recentres
 #endif
 constexpr float PQ_LIMIT = 8.0779357e-28f * (float)(1u << SKB_PQ_SLACK);   // 2^(SLACK - 90)
 static_assert(PQ_CH <= 32 && PQ_CAP <= 256 && SG == 16, "PQ chunk layout");
 __host__ __device__ constexpr bool pq_mode(int D, int Q) { return SKB_PQ && D >= SKB_PQ_MIN_D && Q == 1 && tile_points(D) == 64; }
-__host__ __device__ constexpr int pq_qstride(int D) { return (D + 2) & ~1; }          // u64 words per query row ({z,z} x D, {-m,-m})
+__host__ __device__ constexpr int pq_qstride(int D) { return (D + 4) & ~3; }          // floats per query row: z[0..D), -m, padding to 16 B
 __host__ __device__ constexpr size_t pq_smem_bytes(int D)
 {
-    return (size_t)nstage(D) * stage_floats(D) * 4 + (size_t)nstage(D) * 16 + (size_t)32 * pq_qstride(D) * 8 +
+    return (size_t)nstage(D) * stage_floats(D) * 4 + (size_t)nstage(D) * 16 + (size_t)32 * pq_qstride(D) * 4 +
            (size_t)32 * PQ_ROW * 4 + (size_t)PQ_CAP * 4 + (size_t)PQ_CAP + 16;
 }
 
-// acc - m for this lane's two points against the query row in shared memory
+// acc - m for this lane's two points against the query row in shared memory.  The row holds plain floats:
+// ptxas folds pk(z, z) into the scalar-broadcast operand form of FADD2 / FFMA2 (`R.F32`), so duplicated
+// pairs would only cost shared memory, LDS slots and registers.
 template <int D>
-__device__ __forceinline__ void pq_acc(const u64* __restrict__ qrow, const u64 (&p2)[D], float& a0, float& a1)
+__device__ __forceinline__ void pq_acc(const float* __restrict__ qrow, const u64 (&p2)[D], float& a0, float& a1)
 {
     constexpr int QS = pq_qstride(D);
-    u64 r[QS];
+    float r[QS];
 #pragma unroll
-    for (int k = 0; k < QS; k += 2) {
-        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(qrow + k);
-        r[k] = v.x; r[k + 1] = v.y;
+    for (int k = 0; k < QS; k += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(qrow + k);
+        r[k] = v.x; r[k + 1] = v.y; r[k + 2] = v.z; r[k + 3] = v.w;
     }
-    u64 acc = r[D];
+    u64 acc = pk(r[D], r[D]);
 #pragma unroll
     for (int k = 0; k < D; k++) {
-        const u64 dz = sub2(r[k], p2[k]);
+        const u64 dz = sub2(pk(r[k], r[k]), p2[k]);
         acc = fma2(dz, dz, acc);
     }
     upk(acc, a0, a1);
 }
 
-// fold row `row` of the fp32 partials into a double, fixed order, and clear it
+// fold row `row` of the fp32 partials into a double, fixed (lane) order, and clear it
 __device__ __forceinline__ double pq_fold_row(float* __restrict__ part, int row)
 {
     float* p = part + row * PQ_ROW;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
     for (int l = 0; l < 32; l += 4) {
-        s0 += (double)p[l]; s1 += (double)p[l + 1]; s2 += (double)p[l + 2]; s3 += (double)p[l + 3];
-        p[l] = 0.f; p[l + 1] = 0.f; p[l + 2] = 0.f; p[l + 3] = 0.f;
+        s0 += (double)p[l ^ row]; s1 += (double)p[(l + 1) ^ row]; s2 += (double)p[(l + 2) ^ row]; s3 += (double)p[(l + 3) ^ row];
+        p[l ^ row] = 0.f; p[(l + 1) ^ row] = 0.f; p[(l + 2) ^ row] = 0.f; p[(l + 3) ^ row] = 0.f;
     }
     return __dadd_rn(__dadd_rn(s0, s1), __dadd_rn(s2, s3));
 }
@@ -708,7 +717,7 @@ __device__ __forceinline__ double pq_fold_row(float* __restrict__ part, int row)
 // The score kernel.  grid = (query blocks, jobs, training splits), block = NT threads.
 // ---------------------------------------------------------------------------------------------
 template <int D, int Q>
-__global__ void __launch_bounds__(NT, (Q == queries_per_thread(D) ? min_blocks_per_sm(D) : (D <= 4 ? 2 : (D <= 8 ? 3 : 4))) * (128 / NT))
+__global__ void __launch_bounds__(NT, (Q == queries_per_thread(D) ? min_blocks_per_sm(D) : (SKB_DENSE_QMUL > 1 ? 2 : (D <= 4 ? 2 : (D <= 8 ? 3 : 4)))) * (128 / NT))
 skb_score_kernel(const __grid_constant__ ScoreLaunch L)
 {
     constexpr int QB = NT * Q;
@@ -749,7 +758,7 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
     for (int w = tid; w < nwords; w += NT) need_bits[w] = 0u;
     __syncthreads();
 
-    u64 q2[Q][D];
+    float q2[Q][D];
     load_queries<D, Q>(job, kde, qbase, tid, M, q2);
 
     // ---- main loop over this split's tiles -----------------------------------------------------
@@ -760,9 +769,9 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
     // absorbed without action; beyond that the SUB-point block overflows and is re-run once.
     float mref[Q];          // integer-valued reference exponent per query
     double S[Q];            // fp64 running sum at reference mref:  sum_j w_j 2^(-acc_j) = S * 2^(-mref)
-    u64 nm2[Q];
+    float nm2[Q];
 #pragma unroll
-    for (int q = 0; q < Q; q++) { mref[q] = 0.f; S[q] = 0.0; nm2[q] = pk(0.f, 0.f); }
+    for (int q = 0; q < Q; q++) { mref[q] = 0.f; S[q] = 0.0; nm2[q] = 0.f; }
 
     const int lane = tid & 31;
     unsigned n_rerun = 0, n_blocks = 0, n_culled = 0, n_visited = 0;
@@ -789,7 +798,7 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
                     float lb = 0.f;
 #pragma unroll
                     for (int k = 0; k < D; k++) {
-                        float zq, dup; upk(q2[q][k], zq, dup);
+                        const float zq = q2[q][k];
                         const float gap = fmaxf(fmaxf(lo[k] - zq, zq - hi[k]), 0.f);
                         lb = fmaf(gap, gap, lb);
                     }
@@ -814,7 +823,7 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
                     float lb = 0.f;
 #pragma unroll
                     for (int k = 0; k < D; k++) {
-                        float zq, dup; upk(q2[q][k], zq, dup);
+                        const float zq = q2[q][k];
                         const float gap = fmaxf(fmaxf(lo[k] - zq, zq - hi[k]), 0.f);
                         lb = fmaf(gap, gap, lb);
                     }
@@ -895,7 +904,7 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
                 float lb = 0.f;
 #pragma unroll
                 for (int k = 0; k < D; k++) {
-                    float zq, dup; upk(q2[q][k], zq, dup);
+                    const float zq = q2[q][k];
                     const float gap = fmaxf(fmaxf(hdr[k] - zq, zq - hdr[D + k]), 0.f);
                     lb = fmaf(gap, gap, lb);
                 }
@@ -949,7 +958,7 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
                             fixable = true;
                             bmin[q] = fminf(bmin[q], mref[q] + floorf(amin[q]));
                             mref[q] += delta;
-                            nm2[q] = pk(-mref[q], -mref[q]);
+                            nm2[q] = -mref[q];
                             double e = (double)delta;
                             if (e < -4000.0) e = -4000.0;
                             S[q] = ldexp(S[q], (int)e);
@@ -973,7 +982,7 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
             if (mref[q] - want >= 8.f) {
                 S[q] = ldexp(S[q], (int)fmaxf(want - mref[q], -4000.f));
                 mref[q] = want;
-                nm2[q] = pk(-want, -want);
+                nm2[q] = -want;
             }
         }
         __syncwarp();
@@ -1012,8 +1021,8 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
     float* stages = reinterpret_cast<float*>(smem_raw);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NSTAGE * STAGE_BYTES);
     uint64_t* empty_bar = full_bar + NSTAGE;
-    u64* rows = reinterpret_cast<u64*>(empty_bar + NSTAGE);           // 32 query rows: {z,z} x D, {-m,-m}
-    float* part = reinterpret_cast<float*>(rows + 32 * QS);           // part[query][lane]
+    float* rows = reinterpret_cast<float*>(empty_bar + NSTAGE);       // 32 query rows: z[0..D), -m
+    float* part = rows + 32 * QS;                                     // part[query][lane ^ query]
     unsigned* lmask = reinterpret_cast<unsigned*>(part + 32 * PQ_ROW);   // work list: query mask ...
     unsigned char* ltile = reinterpret_cast<unsigned char*>(lmask + PQ_CAP);   // ... and tile offset in the chunk
     __shared__ int s_last[32 / FB];
@@ -1032,17 +1041,17 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
     }
     __syncwarp();
 
-    u64 q2[Q][D];
+    float q2[Q][D];
     load_queries<D, Q>(job, kde, qbase, lane, M, q2);
     float mref[Q], bmin[Q];
     double S[Q];
-    u64 nm2[Q];
-    mref[0] = 0.f; S[0] = 0.0; nm2[0] = pk(0.f, 0.f);
+    float nm2[Q];
+    mref[0] = 0.f; S[0] = 0.0; nm2[0] = 0.f;
     home_reference<D, Q>(kde, ntiles, q2, bmin, mref, nm2);
 
 #pragma unroll
     for (int k = 0; k < D; k++) rows[lane * QS + k] = q2[0][k];
-    rows[lane * QS + D] = nm2[0];
+    rows[lane * QS + D] = -mref[0];
     for (int l = 0; l < 32; l++) part[lane * PQ_ROW + l] = 0.f;
     __syncwarp();
 
@@ -1073,7 +1082,7 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
         {
             float zq[D];
 #pragma unroll
-            for (int k = 0; k < D; k++) { float dup; upk(q2[0][k], zq[k], dup); }
+            for (int k = 0; k < D; k++) zq[k] = q2[0][k];
             if (cull) {
                 const float* b = cbx + (size_t)(s_base / PQ_CH) * 2 * D;
                 float lb = 0.f;
@@ -1140,15 +1149,15 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
                 const bool on = qm != 0u;
                 const int i = on ? __ffs(qm) - 1 : 0;
                 qm &= qm - 1u;                                            // 0 stays 0
-                const u64* qrow = rows + i * QS;
+                const float* qrow = rows + i * QS;
                 float lb = 0.f;
 #pragma unroll
                 for (int k = 0; k < D; k++) {
-                    const float zq = reinterpret_cast<const float*>(qrow + k)[0];
+                    const float zq = qrow[k];
                     const float gap = fmaxf(fmaxf(lo[k] - zq, zq - hi[k]), 0.f);
                     lb = fmaf(gap, gap, lb);
                 }
-                const float negm = reinterpret_cast<const float*>(qrow + D)[0];
+                const float negm = qrow[D];
                 if (on && (!cull || !(lb + negm > CULL_MARGIN))) tmask |= 1u << i;
             }
             const unsigned nz = __ballot_sync(FULL, tmask != 0u);
@@ -1204,8 +1213,8 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
                         S[0] += pq_fold_row(part, i);
                         S[0] = ldexp(S[0], (int)fmaxf(delta, -4000.f));
                         mref[0] += delta;
-                        nm2[0] = pk(-mref[0], -mref[0]);
-                        rows[i * QS + D] = nm2[0];
+                        nm2[0] = -mref[0];
+                        rows[i * QS + D] = -mref[0];
                     }
                     __syncwarp();
                     pq_acc<D>(rows + i * QS, p2, a0, a1);
@@ -1215,34 +1224,39 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
                 return 0.f;
             };
 
-            while (mask) {
-                const int i0 = __ffs(mask) - 1;
-                mask &= mask - 1u;
-                if (mask) {
-                    const int i1 = __ffs(mask) - 1;
-                    mask &= mask - 1u;
-                    float a0, a1, b0, b1;
-                    float pa = part[i0 * PQ_ROW + lane];                    // issued early: off the critical path
-                    float pb = part[i1 * PQ_ROW + lane];
-                    pq_acc<D>(rows + i0 * QS, p2, a0, a1);
-                    pq_acc<D>(rows + i1 * QS, p2, b0, b1);
-                    float ta = __fmaf_rn(w1, ex2_neg(a1), __fmul_rn(w0, ex2_neg(a0)));
-                    float tb = __fmaf_rn(w1, ex2_neg(b1), __fmul_rn(w0, ex2_neg(b0)));
-                    if (__any_sync(FULL, !(ta < PQ_LIMIT) || !(tb < PQ_LIMIT))) {
-                        if (__any_sync(FULL, !(ta < PQ_LIMIT))) { ta = recentre(i0, a0, a1); pa = part[i0 * PQ_ROW + lane]; }
-                        if (__any_sync(FULL, !(tb < PQ_LIMIT))) { tb = recentre(i1, b0, b1); pb = part[i1 * PQ_ROW + lane]; }
-                    }
-                    part[i0 * PQ_ROW + lane] = pa + ta;
-                    part[i1 * PQ_ROW + lane] = pb + tb;
-                } else {
-                    float a0, a1;
-                    float pa = part[i0 * PQ_ROW + lane];
-                    pq_acc<D>(rows + i0 * QS, p2, a0, a1);
-                    float ta = __fmaf_rn(w1, ex2_neg(a1), __fmul_rn(w0, ex2_neg(a0)));
-                    if (__any_sync(FULL, !(ta < PQ_LIMIT))) { ta = recentre(i0, a0, a1); pa = part[i0 * PQ_ROW + lane]; }
-                    part[i0 * PQ_ROW + lane] = pa + ta;
+            // NQ queries of the mask per step: independent chains for the FMA / SFU latencies
+            auto eval = [&](auto nqc) {
+                constexpr int NQ = decltype(nqc)::value;
+                int idx[NQ];
+                float pa[NQ], a0[NQ], a1[NQ], t[NQ];
+#pragma unroll
+                for (int n = 0; n < NQ; n++) { idx[n] = __ffs(mask) - 1; mask &= mask - 1u; }
+#pragma unroll
+                for (int n = 0; n < NQ; n++) pa[n] = part[idx[n] * PQ_ROW + (lane ^ idx[n])];   // issued early: off the critical path
+#pragma unroll
+                for (int n = 0; n < NQ; n++) pq_acc<D>(rows + idx[n] * QS, p2, a0[n], a1[n]);
+                bool bad = false;
+#pragma unroll
+                for (int n = 0; n < NQ; n++) {
+                    t[n] = __fmaf_rn(w1, ex2_neg(a1[n]), __fmul_rn(w0, ex2_neg(a0[n])));
+                    bad |= !(t[n] < PQ_LIMIT);
                 }
-            }
+                if (__any_sync(FULL, bad)) {
+#pragma unroll
+                    for (int n = 0; n < NQ; n++)
+                        if (__any_sync(FULL, !(t[n] < PQ_LIMIT))) {
+                            t[n] = recentre(idx[n], a0[n], a1[n]);
+                            pa[n] = part[idx[n] * PQ_ROW + (lane ^ idx[n])];
+                        }
+                }
+#pragma unroll
+                for (int n = 0; n < NQ; n++) part[idx[n] * PQ_ROW + (lane ^ idx[n])] = pa[n] + t[n];
+            };
+#if SKB_PQ_UNROLL >= 4
+            while (__popc(mask) >= 4) eval(std::integral_constant<int, 4>{});
+#endif
+            while (__popc(mask) >= 2) eval(std::integral_constant<int, 2>{});
+            if (mask) eval(std::integral_constant<int, 1>{});
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(&empty_bar[s]);
