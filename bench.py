@@ -323,6 +323,12 @@ def run_ours(args):
     launches = lib.skb_launch_count() - launches0
     ms_total = skd.timed_max_ms(e0.elapsed_time(e1), device=dev)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    kernel_ms_ranks = [kernel_ms]
+    if world > 1:                                        # rank skew diagnostic: each rank's mean score-launch time
+        kt = torch.tensor([kernel_ms], dtype=torch.float64, device=dev)
+        kts = [torch.zeros_like(kt) for _ in range(world)]
+        dist.all_gather(kts, kt)
+        kernel_ms_ranks = [round(float(k.item()), 2) for k in kts]
     clk = clocks.stop(t_wall0, t_wall1)
     accepted = skd.allreduce_sum_scalar(accepted_local, device=dev)
 
@@ -441,7 +447,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "ms_per_step": e2e_ms / args.steps, "api": "skysampler_b200.pipeline.RatioSampler.run_host (pinned host batches in, accept flags + counts out, H2D overlapped)",
                     "clocks": clk2},
-            "kernel_ms_each_step": [round(a.elapsed_time(b), 2) for a, b in kev],
+            "kernel_ms_each_step": [round(a.elapsed_time(b), 2) for a, b in kev], "kernel_ms_mean_per_rank": kernel_ms_ranks,
             "gpu_launches": int(launches),
             "roofline": roof,
         }
