@@ -402,3 +402,75 @@ def test_handles_release_device_memory():
     torch.cuda.synchronize()
     free1, _ = torch.cuda.mem_get_info()
     assert free0 - free1 < 64 * 2 ** 20, (free0, free1)
+
+
+# ---- d >= 5 runs the per-query-culling (PQ) kernel: the edge cases above again, in high dimension ----
+
+@pytest.mark.parametrize("d", [5, 8, 12])
+def test_pq_disjoint_clusters_void_and_far_queries(d):
+    """Queries in the void between clusters and far outside have a home tile that is nowhere near their
+    nearest neighbour: the reference has to move (recentre path) and nothing may under/overflow."""
+    rs = np.random.RandomState(70 + d)
+    off = np.zeros(d); off[0] = 4.0
+    a = rs.normal(size=(20000, d)) * 0.2 + off
+    b = rs.normal(size=(20000, d)) * 0.2 - off
+    z = np.vstack([a, b]); rs.shuffle(z)
+    w = rs.uniform(0.2, 3.0, len(z))
+    q = np.vstack([a[:3000] + 0.05 * rs.normal(size=(3000, d)),
+                   0.3 * rs.normal(size=(200, d)),
+                   30.0 * rs.normal(size=(200, d))])
+    kde = _kde(z, w, 0.1)
+    got = kde.score_samples(q); ref = brute64.score(z, w, 0.1, q)
+    assert np.all(np.isfinite(got))
+    _check(got, ref)                      # 1e-4 within 100 nats of the peak, 1e-5 relative beyond
+    kde.close()
+
+
+@pytest.mark.parametrize("n", [1, 3, 64, 65, 1025, 16384 + 7])
+def test_pq_tiny_and_ragged_training_sets(n):
+    """Less than one tile, one super-box, one chunk; one more than each."""
+    rs = np.random.RandomState(n)
+    z = rs.normal(size=(n, 8)); q = 1.2 * rs.normal(size=(777, 8))
+    w = rs.uniform(0.5, 2.0, n) if n > 1 else None
+    kde = _kde(z, w, 0.4)
+    _check(kde.score_samples(q), brute64.score(z, w, 0.4, q))
+    kde.close()
+
+
+def test_pq_degenerate_geometry():
+    rs = np.random.RandomState(43)
+    # all training points identical, 6-D
+    z = np.tile(rs.normal(size=(1, 6)), (900, 1)); q = rs.normal(size=(400, 6))
+    kde = _kde(z, rs.uniform(0.1, 1, 900), 0.3)
+    _check(kde.score_samples(q), brute64.score(z, None, 0.3, q)); kde.close()
+    # thousands of identical queries
+    z1 = rs.normal(size=(5000, 7)); q1 = np.tile(z1[:1] + 0.01, (4000, 1))
+    kde = _kde(z1, None, 0.5)
+    got = kde.score_samples(q1); ref = brute64.score(z1, None, 0.5, q1)
+    assert np.abs(got - ref).max() <= 1e-5 and np.unique(got).size == 1; kde.close()
+    # heavy duplicates and two constant coordinates, 5-D
+    g = np.stack(np.meshgrid(np.arange(6.0), np.arange(6.0), np.arange(3.0), [0.0], [1.0]), -1).reshape(-1, 5)
+    z = np.repeat(g, 50, axis=0); q = np.vstack([g + 0.01, 3.0 + 2.0 * rs.normal(size=(2000, 5))])
+    kde = _kde(z, None, 0.2)
+    _check(kde.score_samples(q), brute64.score(z, None, 0.2, q)); kde.close()
+
+
+def test_pq_forced_training_splits_merge_to_the_same_answer():
+    """SKB_FORCE_NSPLIT > 1 (experiments / few-query launches): every split walks its own tile range and the
+    last-arriving CTA merges the (m, S) partials."""
+    import os
+    from skysampler_b200 import synth
+    x = synth.mixture(8, 150000, 12); m1, pm, comps, std2 = synth.whiten_params(x)
+    z = (x - m1) @ comps.T / std2
+    q = synth.queries(z, 0.1, 5000, 3)
+    kde = _kde(z, None, 0.1)
+    one = kde.score_samples(q)
+    os.environ["SKB_FORCE_NSPLIT"] = "5"
+    try:
+        five = kde.score_samples(q)
+    finally:
+        os.environ.pop("SKB_FORCE_NSPLIT", None)
+    near = one >= one.max() - 100
+    assert np.abs(one - five)[near].max() <= 2e-5
+    _check(five[:300], brute64.score(z, None, 0.1, q[:300]))
+    kde.close()
