@@ -665,6 +665,9 @@ constexpr int PQ_ROW = 32;                        // part[query][lane ^ query]: 
 #ifndef SKB_PQ_UNROLL
 #define SKB_PQ_UNROLL 2       // queries of a tile's mask evaluated per step (2 or 4)
 #endif
+#ifndef SKB_PQ_UNROLL4_MAX_D
+#define SKB_PQ_UNROLL4_MAX_D 6   // ... 4 at a time up to this dimension (short chains, registers to spare: +7 % at d=5)
+#endif
 #ifndef SKB_PQ_SLACK
 #define SKB_PQ_SLACK 3        // a lane term >= 2^(SLACK - REF_BIAS) (a point that much closer than the reference) recentres
 #endif
@@ -1147,8 +1150,8 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
             unsigned tmask = 0u;
             while (__any_sync(FULL, qm != 0u)) {
                 const bool on = qm != 0u;
-                const int i = on ? __ffs(qm) - 1 : 0;
-                qm &= qm - 1u;                                            // 0 stays 0
+                const int i = on ? 31 - __clz(qm) : 0;
+                qm &= ~(1u << i);                                         // 0 stays 0
                 const float* qrow = rows + i * QS;
                 float lb = 0.f;
 #pragma unroll
@@ -1230,7 +1233,7 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
                 int idx[NQ];
                 float pa[NQ], a0[NQ], a1[NQ], t[NQ];
 #pragma unroll
-                for (int n = 0; n < NQ; n++) { idx[n] = __ffs(mask) - 1; mask &= mask - 1u; }
+                for (int n = 0; n < NQ; n++) { idx[n] = 31 - __clz(mask); mask ^= 1u << idx[n]; }   // highest set bit: one FLO, no BREV
 #pragma unroll
                 for (int n = 0; n < NQ; n++) pa[n] = part[idx[n] * PQ_ROW + (lane ^ idx[n])];   // issued early: off the critical path
 #pragma unroll
@@ -1252,10 +1255,9 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
 #pragma unroll
                 for (int n = 0; n < NQ; n++) part[idx[n] * PQ_ROW + (lane ^ idx[n])] = pa[n] + t[n];
             };
-#if SKB_PQ_UNROLL >= 4
-            while (__popc(mask) >= 4) eval(std::integral_constant<int, 4>{});
-#endif
-            while (__popc(mask) >= 2) eval(std::integral_constant<int, 2>{});
+            if constexpr (SKB_PQ_UNROLL >= 4 || D <= SKB_PQ_UNROLL4_MAX_D)
+                while (__popc(mask) >= 4) eval(std::integral_constant<int, 4>{});
+            while (mask & (mask - 1u)) eval(std::integral_constant<int, 2>{});       // at least two bits left
             if (mask) eval(std::integral_constant<int, 1>{});
             __syncwarp();
             if (lane == 0) {
