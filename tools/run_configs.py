@@ -122,7 +122,7 @@ def main():
         if first is None:
             first = qd[:200000:200].cpu().numpy()
         total_ms += timed(lambda: kde.score_samples(qd, out=o), 1)
-    err, nchk = parity(kde, z, None, 0.1, first, n=150)
+    err, nchk = parity(kde, z, None, 0.1, first, n=600)
     out["C4"] = dict(d=16, n_train=n, n_query=nchunks * chunk, h=0.1, kernel_s=total_ms / 1e3, wall_s=time.time() - t0,
                      pairs_per_s=n * float(nchunks * chunk) / total_ms * 1e3, path="direct FP32 kernel (no tensor-core -2XY^T: fails 1e-4, DESIGN.md)",
                      max_abs_dlogp_within_100_nats=err, rows_checked=nchk)
