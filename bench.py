@@ -355,7 +355,7 @@ def run_ours(args):
     clocks2.start()
     time.sleep(0.3)
     e2e_batches = [(q_host[i % nb_host], u_host[i % nb_host]) for i in range(args.steps)]
-    sampler.run_host(e2e_batches[:2])                     # warm-up of the pipelined path (side stream, slots)
+    sampler.run_host(e2e_batches)                         # warm-up of the pipelined path (side stream, slots, pinned result buffers)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -367,6 +367,18 @@ def run_ours(args):
     t_e1 = time.time()
     clk2 = clocks2.stop(t_e0, t_e1)
     e2e_ms = skd.timed_max_ms(f0.elapsed_time(f1), device=dev)
+    # host-path diagnostic: one pinned batch host -> device on an idle GPU (explains e2e on boxes with a slow host path)
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    qd_probe = torch.empty((args.batch, D), dtype=torch.float64, device=dev)
+    qd_probe.copy_(q_host[0], non_blocking=True)
+    torch.cuda.synchronize()
+    h0.record()
+    for b in range(3):
+        qd_probe.copy_(q_host[b % nb_host], non_blocking=True)
+    h1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 3 * args.batch * D * 8 / (h0.elapsed_time(h1) * 1e-3) / 1e9
+    del qd_probe
     e2e_value = pairs_per_step_rank * world * args.steps / (e2e_ms * 1e-3)
     h2d = args.batch * D * 8 + args.batch * 8
     d2h = args.batch + 8
@@ -446,6 +458,7 @@ def run_ours(args):
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "ms_per_step": e2e_ms / args.steps, "api": "skysampler_b200.pipeline.RatioSampler.run_host (pinned host batches in, accept flags + counts out, H2D overlapped)",
+                    "h2d_gbs_idle_gpu": round(h2d_gbs, 2),
                     "clocks": clk2},
             "kernel_ms_each_step": [round(a.elapsed_time(b), 2) for a, b in kev], "kernel_ms_mean_per_rank": kernel_ms_ranks,
             "gpu_launches": int(launches),

@@ -34,8 +34,13 @@ __host__ __device__ constexpr int tile_points(int D) { return D <= 4 ? SKB_TN_LO
 #ifndef SKB_NSTAGE_HI
 #define SKB_NSTAGE_HI 2
 #endif
-// TMA ring depth (shared memory per CTA = depth x tile bytes).  D >= 5 runs the per-query inner loop, whose
-// speed follows the number of resident warps: two stages there keep 16 one-warp CTAs on an SM.
+#ifndef SKB_NSTAGE_PQ
+#define SKB_NSTAGE_PQ 1
+#endif
+// TMA ring depth (shared memory per CTA = depth x tile bytes) of the lanes = queries kernel.  The per-query
+// kernel (D >= 5, culling on) copies a tile into registers on arrival and hands its stage back at once, so
+// ONE stage (SKB_NSTAGE_PQ) already overlaps the next copy with the whole pair loop — and that kernel's speed
+// follows the number of resident warps (one stage: 22 one-warp CTAs per SM at d = 8).
 __host__ __device__ constexpr int nstage(int D) { return D <= 4 ? SKB_NSTAGE : SKB_NSTAGE_HI; }
 #ifndef SKB_NT
 #define SKB_NT 32

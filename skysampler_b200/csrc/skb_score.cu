@@ -646,6 +646,9 @@ __device__ __forceinline__ void finish_queries(const ScoreLaunch& L, const Score
 #ifndef SKB_PQ
 #define SKB_PQ 1
 #endif
+#ifndef SKB_PQ_EPOCH_SHIFT
+#define SKB_PQ_EPOCH_SHIFT 8
+#endif
 #ifndef SKB_TEST_UNROLL
 #define SKB_TEST_UNROLL 4     // tile box tests of the need-bitmap phase (lanes = queries kernel) in flight at once
 #endif
@@ -653,14 +656,14 @@ __device__ __forceinline__ void finish_queries(const ScoreLaunch& L, const Score
 #define SKB_PQ_MIN_D 5
 #endif
 #ifndef SKB_PQ_MINB
-#define SKB_PQ_MINB 16        // launch bound (CTAs per SM) of the PQ kernel for D <= 8
+#define SKB_PQ_MINB 22        // launch bound (CTAs per SM) of the PQ kernel for D <= 8 (96 registers)
 #endif
 #ifndef SKB_PQ_MINB_HI
-#define SKB_PQ_MINB_HI 16     // same for D > 8
+#define SKB_PQ_MINB_HI 20     // same for 8 < D <= 12 (80 registers); D > 12 keeps 16 (128 registers)
 #endif
 constexpr int PQ_CH = CG;                         // one work list per chunk box
 constexpr int PQ_CAP = PQ_CH * SG;                // work-list capacity: every tile of a chunk
-constexpr int PQ_EPOCH_SHIFT = 7;                 // fp32 row partials are folded into fp64 every 128 tile indices
+constexpr int PQ_EPOCH_SHIFT = SKB_PQ_EPOCH_SHIFT;                 // fp32 row partials are folded into fp64 every 256 tile indices
 constexpr int PQ_ROW = 32;                        // part[query][lane ^ query]: conflict-free for both walks
 #ifndef SKB_PQ_UNROLL
 #define SKB_PQ_UNROLL 2       // queries of a tile's mask evaluated per step (2 or 4)
@@ -677,7 +680,7 @@ __host__ __device__ constexpr bool pq_mode(int D, int Q) { return SKB_PQ && D >=
 __host__ __device__ constexpr int pq_qstride(int D) { return (D + 4) & ~3; }          // floats per query row: z[0..D), -m, padding to 16 B
 __host__ __device__ constexpr size_t pq_smem_bytes(int D)
 {
-    return (size_t)nstage(D) * stage_floats(D) * 4 + (size_t)nstage(D) * 16 + (size_t)32 * pq_qstride(D) * 4 +
+    return (size_t)SKB_NSTAGE_PQ * stage_floats(D) * 4 + (size_t)SKB_NSTAGE_PQ * 16 + (size_t)32 * pq_qstride(D) * 4 +
            (size_t)32 * PQ_ROW * 4 + (size_t)PQ_CAP * 4 + (size_t)PQ_CAP + 16;
 }
 
@@ -1003,7 +1006,7 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
 }
 
 template <int D>
-__global__ void __launch_bounds__(32, D <= 8 ? SKB_PQ_MINB : SKB_PQ_MINB_HI)
+__global__ void __launch_bounds__(32, D <= 8 ? SKB_PQ_MINB : (D <= 12 ? SKB_PQ_MINB_HI : 16))
 skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
 {
     constexpr int Q = 1;
@@ -1011,7 +1014,7 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
     constexpr int QS = pq_qstride(D);
     constexpr int STAGE_FLOATS = stage_floats(D);
     constexpr uint32_t STAGE_BYTES = STAGE_FLOATS * sizeof(float);
-    constexpr int NSTAGE = nstage(D);
+    constexpr int NSTAGE = SKB_NSTAGE_PQ;
     constexpr unsigned FULL = 0xffffffffu;
     static_assert(TN == 64 && NT == 32, "PQ: one warp per CTA, two tile points per lane");
 
@@ -1201,6 +1204,12 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
             float w0, w1;
             upk(*reinterpret_cast<const u64*>(tile + D * TN + 2 * lane), w0, w1);
             n_pairs += 2u * __popc(mask);
+            // the tile now lives in registers: hand the stage back and request the tile NSTAGE entries ahead
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&empty_bar[s]);
+                if (e + NSTAGE < cnt) request(it + (unsigned)NSTAGE, tchunk + ltile[e + NSTAGE]);
+            }
 
             // rare: a point >= 8 binades closer than the reference was built for (or a NaN row) — fold the
             // row, move the query's reference to the tile's closest point, re-evaluate
@@ -1259,11 +1268,6 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
                 while (__popc(mask) >= 4) eval(std::integral_constant<int, 4>{});
             while (mask & (mask - 1u)) eval(std::integral_constant<int, 2>{});       // at least two bits left
             if (mask) eval(std::integral_constant<int, 1>{});
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&empty_bar[s]);
-                if (e + NSTAGE < cnt) request(it + (unsigned)NSTAGE, tchunk + ltile[e + NSTAGE]);
-            }
         }
         __syncwarp();                                                      // the list is rebuilt next chunk
     }

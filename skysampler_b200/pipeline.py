@@ -91,7 +91,8 @@ class RatioSampler(object):
         """Pipelined end-to-end pass over a sequence of (rows, uniforms) batches in PINNED host memory:
         the H2D copy of batch i+1 runs on a side stream while batch i is scored, accept flags and accepted
         counts stream back asynchronously, one synchronisation at the end.  Returns (list of pinned uint8
-        flag tensors, list of accepted counts)."""
+        flag tensors, list of accepted counts); the flag tensors are views of a pinned buffer that the next
+        call reuses."""
         batches = list(batches)
         if not batches:
             return [], []
@@ -106,8 +107,13 @@ class RatioSampler(object):
                           self._get("acc_pipe%d" % s, (M,), torch.uint8)))
         ready = [torch.cuda.Event(), torch.cuda.Event()]
         free = [torch.cuda.Event(), torch.cuda.Event()]
-        flags_host = [torch.empty(M, dtype=torch.uint8, pin_memory=True) for _ in batches]
-        counts_host = torch.zeros(len(batches), dtype=torch.int64, pin_memory=True)
+        # pinned result buffers are kept between calls (cudaHostAlloc costs milliseconds and blocks the host)
+        pinned = getattr(self, "_pinned_out", None)
+        if pinned is None or pinned[0].shape[0] < len(batches) or pinned[0].shape[1] != M:
+            pinned = self._pinned_out = (torch.empty((len(batches), M), dtype=torch.uint8, pin_memory=True),
+                                         torch.zeros(len(batches), dtype=torch.int64, pin_memory=True))
+        flags_host = [pinned[0][i] for i in range(len(batches))]
+        counts_host = pinned[1][:len(batches)]
 
         def upload(i):
             qd, ud, _ = slots[i % 2]
