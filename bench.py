@@ -192,6 +192,14 @@ class ClockSampler(object):
         for ln in self.proc.stdout:
             self.rows.append((time.time(), ln.strip()))
 
+    def wait_ready(self, timeout=8.0):
+        """Block until nvidia-smi has delivered its first sample: its start-up attaches to the driver and can stall
+        work submission for tens of milliseconds, which must not land inside a timed region."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.05)
+        time.sleep(0.1)
+
     def stop(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -301,7 +309,7 @@ def run_ours(args):
         dist.barrier()
     clocks = ClockSampler(local)
     clocks.start()
-    time.sleep(0.3)
+    clocks.wait_ready()
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = lib.skb_launch_count()
@@ -353,7 +361,7 @@ def run_ours(args):
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clocks2 = ClockSampler(local)
     clocks2.start()
-    time.sleep(0.3)
+    clocks2.wait_ready()
     e2e_batches = [(q_host[i % nb_host], u_host[i % nb_host]) for i in range(args.steps)]
     sampler.run_host(e2e_batches)                         # warm-up of the pipelined path (side stream, slots, pinned result buffers)
     torch.cuda.synchronize()
@@ -365,6 +373,8 @@ def run_ours(args):
     f1.record()
     torch.cuda.synchronize()
     t_e1 = time.time()
+    if os.environ.get("SKB_TRACE_RUN_HOST"):
+        sys.stderr.write("bench e2e: %.2f ms by events, %.2f ms wall\n" % (f0.elapsed_time(f1), (t_e1 - t_e0) * 1e3))
     clk2 = clocks2.stop(t_e0, t_e1)
     e2e_ms = skd.timed_max_ms(f0.elapsed_time(f1), device=dev)
     # host-path diagnostic: one pinned batch host -> device on an idle GPU (explains e2e on boxes with a slow host path)

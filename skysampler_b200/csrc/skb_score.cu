@@ -18,12 +18,17 @@
 //   * two training points ride in one FADD2/FFMA2 (packed fp32x2, one issue slot for two lane ops), which
 //     leaves issue slots for MUFU.EX2 and LDS — measured on B200: 8xFFMA2 + 2xMUFU per loop co-issue at
 //     98% of the FMA peak, the scalar form is issue-bound at 80%.
-// Culling.  Training tiles are kd-tree leaves with bounding boxes and a warp's queries are Morton
-// neighbours: a tile whose box is > 128 binades beyond every reference of the warp has only terms that
-// flush to zero in the arithmetic above and is skipped (never even loaded when the whole CTA agrees).
+// Culling.  Training tiles are kd-tree leaves with bounding boxes (three levels: tile, super-box of 16 tiles,
+// chunk of 16 super-boxes) and a warp's queries are Morton neighbours: a tile whose box is > 128 binades
+// beyond a query's reference has only terms that flush to zero in the arithmetic above and is skipped.
+// Two kernels:
+//   skb_score_kernel<D,Q>   lanes = queries (Q whole queries per thread, tile words broadcast by LDS.128, no
+//                           cross-lane reduction); a tile is evaluated when ANY query of the warp needs it.
+//                           Used for D <= 4 and, with larger Q, whenever culling is off.
+//   skb_score_pq_kernel<D>  D >= 5: lanes = two training points each; box tests one tile per lane; only the
+//                           queries that need a tile are evaluated (see the comment above the kernel).
 // Data movement.  One warp per CTA; its needed tiles arrive in shared memory through a private ring of
-// 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx); all lanes read the same tile words
-// (LDS.128 broadcast), each thread owning Q whole queries, so no cross-lane reduction exists.
+// 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx).
 #include "skb_internal.h"
 #include <math.h>
 #include <type_traits>

@@ -8,6 +8,8 @@ supplies device buffers, pinned host buffers and the stream; the arithmetic is a
 """
 import ctypes as C
 
+import os
+
 import numpy as np
 import torch
 
@@ -124,17 +126,36 @@ class RatioSampler(object):
                 ud.copy_(batches[i][1], non_blocking=True)
                 ready[i % 2].record(side)
 
+        trace = [] if os.environ.get("SKB_TRACE_RUN_HOST") else None      # debug: per-batch device timeline on stderr
+        if trace is not None:
+            import sys, time
+            t_h0 = time.perf_counter()
         upload(0)
+        if trace is not None:
+            sys.stderr.write("run_host: first upload enqueued after %.2f ms on the host\n" % ((time.perf_counter() - t_h0) * 1e3))
         for i in range(len(batches)):
             if i + 1 < len(batches):
                 upload(i + 1)
             qd, ud, keep = slots[i % 2]
+            if trace is not None:
+                trace.append([torch.cuda.Event(enable_timing=True) for _ in range(3)])
+                trace[-1][0].record(main)
             main.wait_event(ready[i % 2])
+            if trace is not None:
+                trace[-1][1].record(main)
             accept, _, _, _ = self.score_accept(qd, ud, stream=main)
+            if trace is not None:
+                trace[-1][2].record(main)
+                if i == 0:
+                    sys.stderr.write("run_host: first score enqueued after %.2f ms on the host\n" % ((time.perf_counter() - t_h0) * 1e3))
             keep.copy_(accept)
             self.compact(keep, qd, stream=main, sync_count=False)
             free[i % 2].record(main)
             flags_host[i].copy_(keep, non_blocking=True)
             counts_host[i:i + 1].copy_(keep.sum(dtype=torch.int64).reshape(1), non_blocking=True)
         main.synchronize()
+        if trace is not None:
+            for i, (a, b, c) in enumerate(trace):
+                sys.stderr.write("run_host batch %d: wait for rows %.2f ms, score %.2f ms, since first batch %.2f ms\n" % (
+                    i, a.elapsed_time(b), b.elapsed_time(c), trace[0][0].elapsed_time(c)))
         return flags_host, [int(c) for c in counts_host]
