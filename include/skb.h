@@ -24,8 +24,10 @@
  *   - every (query, training) pair is accounted for exactly as the all-pairs sum in fp32 terms /
  *     fp64 log-sum-exp would: tiles of training points whose bounding box proves that all their terms
  *     flush to zero are skipped (kd-ordered tiles, Morton-ordered queries).  SKB_NO_CULL=1 in the
- *     environment evaluates every pair (diagnostics).  A query's result never depends on the other rows
- *     of the call: any batching / sharding of the query table is bit-identical.
+ *     environment evaluates every pair (diagnostics; it runs a different kernel, so its results agree
+ *     with the default path to fp32 summation-order rounding — a few 1e-5 in log p — not in bits).  A
+ *     query's result never depends on the other rows of the call: any batching / sharding of the query
+ *     table is bit-identical.
  *   - one call at a time per handle: scratch buffers are owned by the handle.
  */
 #ifndef SKB_H
