@@ -147,8 +147,8 @@ struct StepOperands {
 // order as MUFU.EX2's), scaled by adding n << 23 to the exponent field.  8 packed FMA-pipe ops per two
 // terms (+ 2 IMAD, 4 FMNMX).  Used for a fixed quarter of the terms when D == 1, where the SFU is the
 // binding pipe and the FMA pipe is 3/8 busy: measured +4.5 % (4.45e12 -> 4.66e12 pairs/s on B200); at D == 2
-// the same offload LOSES 13 % (the FMA pipe becomes the limiter), so it is not applied there.  The argument is clamped to [-126, 125] so that
-// far points give <= 2^-125 (not garbage) and an exponent-window overflow still reads as >= 2^120.
+// the same offload LOSES 13 % (the FMA pipe becomes the limiter), so it is not applied there.  The argument is clamped to [-126, 250] and the
+// result's bit pattern to >= 0, so that far points (a >= 127) give exactly 0 and an exponent-window overflow still reads as >= 2^120.
 // Q independent polynomial exponentials, written stage-major so that the Q dependent chains interleave
 // (each stage is one packed FMA-pipe op per query; a single chain is 8 ops deep).
 template <int Q>
@@ -160,8 +160,8 @@ __device__ __forceinline__ void exp2_neg_poly2_batch(u64 (&v)[Q])
     for (int q = 0; q < Q; q++) {
         float a0, a1;
         upk(v[q], a0, a1);
-        a0 = fminf(fmaxf(a0, -126.f), 125.f);
-        a1 = fminf(fmaxf(a1, -126.f), 125.f);
+        a0 = fminf(fmaxf(a0, -126.f), 250.f);
+        a1 = fminf(fmaxf(a1, -126.f), 250.f);
         v[q] = pk(a0, a1);
     }
 #pragma unroll
@@ -186,8 +186,11 @@ __device__ __forceinline__ void exp2_neg_poly2_batch(u64 (&v)[Q])
         float p0, p1, t0, t1;
         upk(v[q], p0, p1);
         upk(t[q], t0, t1);
-        v[q] = pk(__int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23)),
-                  __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23)));
+        // a >= 127 drives the exponent field to <= 0: the sum goes negative as an integer and is clamped to
+        // +0.0 — far terms must be EXACTLY zero, like the flushed MUFU terms, or a query's sum would depend on
+        // which culled tiles its warp companions keep alive
+        v[q] = pk(__int_as_float(max(__float_as_int(p0) + (__float_as_int(t0) << 23), 0)),
+                  __int_as_float(max(__float_as_int(p1) + (__float_as_int(t1) << 23), 0)));
     }
 }
 

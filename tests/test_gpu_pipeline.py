@@ -247,3 +247,46 @@ def test_pipelined_host_batches_equal_resident_steps():
         rows, n = s.step(qs[i].cuda(), us[i].cuda())
         assert n == counts[i] and np.array_equal(rows.cpu().numpy(), qs[i].numpy()[flags[i].numpy().astype(bool)])
     ka.close(); kb.close()
+
+
+@pytest.mark.xfail(strict=False, reason="round-1 open item: in a mixed group (6-D + 2-D + 1-D) one member's log p was not bit-identical "
+                   "to its single-KDE call (parity fine).  Suspected cause, fixed after the last GPU run of the round and so "
+                   "unconfirmed: at d=1 the polynomial-exp terms of far points were 2^-125 instead of exactly 0, which made a "
+                   "query's sum depend on the culled tiles its warp companions keep alive (DESIGN.md section 7)")
+def test_fused_ratio_accept_mixes_both_score_kernels():
+    """A KDE group with a 6-D member (per-query-culling kernel) and 2-D / 1-D members (lanes = queries kernel):
+    the launches share the visit order and the arrival counters; whichever CTA arrives last finalises."""
+    from skysampler_b200 import emulator, KDEContainer, synth
+    from oracle import brute64
+    rs = np.random.RandomState(5)
+    n = 6000
+    names = ["C0", "C1", "C2", "C3", "C4", "LOGR"]
+    tab = pd.DataFrame(np.column_stack([synth.mixture(5, n, 43), 0.3 * rs.normal(size=n)]), columns=names)
+    conts, colsets = [], [names, ["C0", "C1"], ["LOGR"]]
+    for k, cs in enumerate(colsets):
+        x = tab[cs].values + 0.1 * rs.normal(size=(n, len(cs)))
+        c = KDEContainer(pd.DataFrame(x, columns=cs), pd.Series(synth.wide_weights(n, 70 + k)), seed=80 + k)
+        c.standardize_data(); c.construct_kde(0.15)
+        conts.append(c)
+    m = 7001
+    prop = pd.DataFrame(tab.values[rs.randint(0, n, m)] + 0.15 * rs.normal(size=(m, 6)), columns=names)
+    u = rs.uniform(size=m)
+    out = emulator.score_group(conts, colsets, prop, sign=[1, -1, -1], log_m=np.log(20.0), u=u, band=2e-4)
+    refs, mismatch = [], []
+    for c, cs, lp in zip(conts, colsets, out["logp"]):
+        ref = brute64.score(np.asarray(c._data), np.asarray(c.weights), 0.15, np.asarray(c.pca_transform(prop[cs])))
+        near = ref >= ref.max() - 100
+        assert np.abs(lp - ref)[near].max() <= 1e-4
+        single, _ = c.score_samples(prop[cs])
+        if not np.array_equal(single, lp):                     # group and single paths: same bits
+            mismatch.append((len(cs), int((single != lp).sum()), float(np.abs(single - lp).max())))
+        refs.append(ref)
+    lr = oaccept.log_ratio(refs, [np.log(abs(c._jacobian_det)) for c in conts], [1, -1, -1], np.log(20.0))
+    assert np.abs(out["log_ratio"] - lr).max() <= 3e-4
+    band = np.abs(lr - np.log(u)) <= 4e-4
+    assert np.array_equal(out["accept"][~band], (np.log(u) < lr)[~band])
+    again = emulator.score_group(conts, colsets, prop, sign=[1, -1, -1], log_m=np.log(20.0), u=u, band=2e-4)
+    assert np.array_equal(again["log_ratio"], out["log_ratio"])    # counters self-reset
+    for c in conts:
+        c.drop_kde()
+    assert not mismatch, "(dimension, rows that differ, max |d log p|) per member: %r" % (mismatch,)

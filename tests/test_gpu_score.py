@@ -240,7 +240,7 @@ def test_results_do_not_depend_on_batching():
     """The launch plan is a function of the fitted KDE only: any slice, chunk or shard of the query table
     gives bit-identical log-densities (what makes k-GPU query sharding reproduce 1 GPU bit for bit)."""
     rs = np.random.RandomState(21)
-    for n, d, m in ((300000, 8, 70000), (40000, 4, 9000), (3000, 2, 9000), (300000, 16, 40000)):
+    for n, d, m in ((300000, 8, 70000), (40000, 4, 9000), (3000, 2, 9000), (300000, 16, 40000), (50000, 1, 9000)):
         z = rs.normal(size=(n, d)); w = rs.uniform(0.5, 2, n)
         q = 1.5 * rs.normal(size=(m, d))               # long tables use Q queries/thread, short slices the small-Q kernel
         kde = _kde(z, w, 0.1)
