@@ -127,3 +127,31 @@ def test_accept_restatement_matches_read_concentric():
         assert np.array_equal((np.log(u) < lr)[~band], np.asarray(mask)[~band])
         samples = g["samples_exact"]
         np.testing.assert_array_equal(samples[np.asarray(mask)], g["accepted_rows_m%d" % m_factor])
+
+
+def test_fp32_window_model_meets_the_parity_bar_and_culling_is_exact():
+    """The kernels' fp32 scheme restated in numpy (oracle/fp32_model.py): exponent window 90 binades below the
+    nearest point, ftz below 2^-126, fp32 lane partials, fp64 folds.  It must (1) meet the 1e-4 parity bar
+    against the fp64 oracle within 100 nats of the peak, for clustered data and for tail queries, and
+    (2) give the same BITS with and without tile culling — a culled tile contributes exactly nothing."""
+    from oracle import brute64, fp32_model
+    rs = np.random.RandomState(12)
+    for d, h in ((2, 0.1), (5, 0.1), (8, 0.15)):
+        centres = 3.0 * rs.normal(size=(4, d))
+        z = np.vstack([c + 0.4 * rs.normal(size=(700, d)) for c in centres])
+        order = np.lexsort(z.T[::-1])                       # any spatially coherent order makes boxes that cull
+        z = z[order]
+        w = rs.uniform(0.2, 3.0, len(z))
+        q = np.vstack([z[rs.randint(0, len(z), 120)] + h * rs.normal(size=(120, d)),
+                       2.0 * z[rs.randint(0, len(z), 20)],
+                       40.0 * rs.normal(size=(10, d))])
+        ref = brute64.score(z, w, h, q)
+        got, skipped = fp32_model.score(z, w, h, q, cull=True)
+        dense, none = fp32_model.score(z, w, h, q, cull=False)
+        assert none == 0 and skipped > 0.3 * len(q) * (len(z) // 64), (d, skipped)
+        assert np.array_equal(got, dense)                     # culling is exact
+        assert np.all(np.isfinite(got))
+        near = ref >= ref.max() - 100.0
+        assert np.abs(got - ref)[near].max() <= 1e-4, (d, np.abs(got - ref)[near].max())
+        far = ~near
+        assert (np.abs(got - ref)[far] / np.abs(ref[far])).max() <= 1e-5
