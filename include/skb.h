@@ -28,7 +28,8 @@
  *     with the default path to fp32 summation-order rounding — a few 1e-5 in log p — not in bits).  A
  *     query's result never depends on the other rows of the call: any batching / sharding of the query
  *     table is bit-identical.
- *   - one call at a time per handle: scratch buffers are owned by the handle.
+ *   - handles own no scratch: per-call buffers come from the CUDA stream-ordered memory pool on the call's
+ *     stream, so calls on different streams may share a handle.
  */
 #ifndef SKB_H
 #define SKB_H
@@ -90,6 +91,7 @@ int64_t skb_n_train(skb_handle h);
 int     skb_ndim(skb_handle h);
 double  skb_sum_weight(skb_handle h);
 int     skb_device(skb_handle h);
+double  skb_fit_ms(skb_handle h);                   /* device time of the fit inside skb_create (whitening, kd ordering, packing) */
 
 /*
  * score_samples (emulator.py:380-385 -> sklearn _kde.py:252-288 -> kernel_density
@@ -196,7 +198,19 @@ int skb_compact(const uint8_t* flags, int64_t M, const void* rows, int dtype, in
 int skb_measure_pipes(int device, double ms_each, double* fma_lane_per_s, double* ex2_per_s);
 
 /*
- * Diagnostics of the score kernel since the last reset (synchronises the device):
+ * Process-wide diagnostic switches (the release kernels carry no counters and read no environment per call):
+ *   "cull"          1 (default) skip training tiles whose box proves every term flushes to zero; 0 = evaluate
+ *                   every pair with the all-pairs kernel (roofline measurements; agrees to fp32 rounding).
+ *                   The initial value is 0 when SKB_NO_CULL=1 is in the environment at load time.
+ *   "force_nsplit"  > 0: split the training tiles over that many CTAs per query block (experiments).
+ *   "stats"         1: launches made while it is set count evaluated pairs / culled tiles (skb_debug_counters).
+ */
+int skb_set_option(const char* name, int value);
+int skb_get_option(const char* name);               /* -1 for an unknown name */
+
+/*
+ * Diagnostics of the score kernel since the last reset (synchronises the device); all zero unless
+ * skb_set_option("stats", 1) was in effect for the launches of interest:
  *   out4[0] = (query, point) pairs per lane re-run after an exponent-window overflow (warp level)
  *   out4[1] = (query, point) pairs per lane evaluated (warp level): x 32 lanes = pairs evaluated
  *   out4[2] = tiles skipped by the box tests (warp level);  out4[3] = tiles in range (warp level).

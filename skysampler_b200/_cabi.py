@@ -46,6 +46,9 @@ SIGNATURES = {
     "skb_ndim": (C.c_int, [C.c_void_p]),
     "skb_sum_weight": (C.c_double, [C.c_void_p]),
     "skb_device": (C.c_int, [C.c_void_p]),
+    "skb_fit_ms": (C.c_double, [C.c_void_p]),
+    "skb_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "skb_get_option": (C.c_int, [C.c_char_p]),
     "skb_score": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int,
                             C.c_void_p, C.c_void_p]),
     "skb_score_partial": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int,
@@ -135,10 +138,33 @@ def stream_ptr(stream=None):
     return C.c_void_p(int(stream.cuda_stream))
 
 
-def cols_array(cols, d):
+def cols_array(cols, d, ld=None):
     if cols is None:
         return None
     a = np.ascontiguousarray(np.asarray(cols, dtype=np.int32))
     if a.shape != (d,):
         raise ValueError("need %d column indices, got shape %s" % (d, a.shape))
+    if ld is not None and (a.min() < 0 or a.max() >= ld):
+        raise ValueError("column indices %s out of range for a table with %d columns" % (a.tolist(), ld))
     return a
+
+
+def set_option(name, value):
+    """Process-wide diagnostic switch of the library (include/skb.h: "cull", "force_nsplit", "stats")."""
+    check(lib().skb_set_option(name.encode(), int(value)))
+
+
+class option(object):
+    """``with option("cull", 0): ...`` — set a diagnostic switch for a block and restore it afterwards."""
+
+    def __init__(self, name, value):
+        self.name, self.value = name, int(value)
+
+    def __enter__(self):
+        self.prev = lib().skb_get_option(self.name.encode())
+        set_option(self.name, self.value)
+        return self
+
+    def __exit__(self, *exc):
+        set_option(self.name, self.prev)
+        return False

@@ -48,23 +48,48 @@ static bool is_device_ptr(const void* p)
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
-// grow-only device scratch
-struct Scratch {
-    void* p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t bytes, bool zero_new = false)
+// Per-call device scratch from the CUDA stream-ordered memory pool: allocated and freed on the call's
+// stream, so a handle owns no scratch, concurrent calls on different streams never share a buffer, and the
+// pool (release threshold raised at first use) hands the same blocks back call after call.
+struct Arena {
+    cudaStream_t st;
+    void* blocks[24];
+    int n = 0;
+    explicit Arena(cudaStream_t s) : st(s) {}
+    cudaError_t get(void** out, size_t bytes)
     {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return e; }
-        size_t want = bytes + bytes / 4 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) { p = nullptr; return e; }
-        cap = want;
-        if (zero_new) return cudaMemset(p, 0, want);
-        return cudaSuccess;
+        *out = nullptr;
+        if (n >= 24) return cudaErrorMemoryAllocation;
+        cudaError_t e = cudaMallocAsync(out, bytes ? bytes : 16, st);
+        if (e == cudaSuccess) blocks[n++] = *out;
+        return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    ~Arena() { for (int i = 0; i < n; i++) cudaFreeAsync(blocks[i], st); }
 };
+
+static void raise_pool_threshold(int device)
+{
+    static bool done[64] = {false};
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;               // keep freed blocks cached instead of returning them to the OS
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+    done[device] = true;
+}
+
+// Process-wide diagnostic switches (skb_set_option).  Defaults come from the environment ONCE, at load.
+static int env_int(const char* name, int dflt)
+{
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+static std::atomic<int> g_opt_cull{env_int("SKB_NO_CULL", 0) ? 0 : 1};
+static std::atomic<int> g_opt_nsplit{env_int("SKB_FORCE_NSPLIT", 0)};
+static std::atomic<int> g_opt_stats{0};
+static unsigned long long* g_stats_dev[64] = {nullptr};
 
 }  // namespace skb
 
@@ -78,14 +103,10 @@ struct skb_kde {
     float* tiles = nullptr;
     float* boxes = nullptr;
     float* sboxes = nullptr;
-    int* perm = nullptr;       // fit-time only
     double* zt64 = nullptr;
     double* cumsum = nullptr;
-    Scratch partial;           // [nsplit][M] double2
-    Scratch counters;          // [ceil(M/FB)] int, zero between calls
-    Scratch q_stage, out_stage, aux_stage, flag_stage, sort_stage;
-    Scratch small;             // 2 x u64 device counters
     double log_wmax = 0.0;
+    float fit_ms = 0.f;        // device time of the fit (whitening, kd ordering, packing)
 };
 
 namespace skb {
@@ -101,50 +122,17 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-// ---- kd-tree ordering (host, fit time) ----------------------------------------------------------
-// Recursive median split along the widest coordinate; the left part always takes a whole number of
-// tiles (of super-boxes higher up) so that every tile except the last is a full leaf of TN points.
-static void kd_order(const float* z, int D, int* idx, long long n)
-{
-    const long long TN = tile_points(D);
-    if (n <= TN) return;
-    float lo[SKB_MAXD], hi[SKB_MAXD];
-    for (int k = 0; k < D; k++) { lo[k] = INFINITY; hi[k] = -INFINITY; }
-    for (long long i = 0; i < n; i++) {
-        const float* p = z + (size_t)idx[i] * D;
-        for (int k = 0; k < D; k++) { if (p[k] < lo[k]) lo[k] = p[k]; if (p[k] > hi[k]) hi[k] = p[k]; }
-    }
-    int kbest = 0;
-    for (int k = 1; k < D; k++) if (hi[k] - lo[k] > hi[kbest] - lo[kbest]) kbest = k;
-    // split in whole chunks (CG super-boxes) while the node is larger than one, then in whole super-boxes (SG
-    // tiles), then in whole tiles: every aligned run of SG tiles / CG super-boxes is then a kd subtree, so
-    // its union box is as tight as the tree allows
-    const long long unit = n > (long long)CG * SG * TN ? (long long)CG * SG * TN : (n > (long long)SG * TN ? (long long)SG * TN : TN);
-    const long long nunit = (n + unit - 1) / unit;
-    const long long nl = ((nunit + 1) / 2) * unit;        // 0 < nl < n because nunit >= 2
-    std::nth_element(idx, idx + nl, idx + n,
-                     [z, D, kbest](int a, int b) { return z[(size_t)a * D + kbest] < z[(size_t)b * D + kbest]; });
-    kd_order(z, D, idx, nl);
-    kd_order(z, D, idx + nl, n - nl);
-}
-
 // ---- launch planning --------------------------------------------------------------------------
 
 // Training-set splits of a launch (blockIdx.z).  Never a function of the number of query rows: the
 // arithmetic a query sees must be the same whatever batch, chunk or GPU it lands in, so that results
 // are bit-identical under any query sharding.
-static bool cull_enabled()
-{
-    const char* e = getenv("SKB_NO_CULL");       // SKB_NO_CULL=1: evaluate every pair (roofline measurements)
-    return !(e && atoi(e) != 0);
-}
+static bool cull_enabled() { return g_opt_cull.load(std::memory_order_relaxed) != 0; }
 
 static int plan_nsplit(const skb_kde* h, long long /*M*/, int /*njobs*/)
 {
-    if (const char* f = getenv("SKB_FORCE_NSPLIT")) {      // experiments only
-        int v = atoi(f);
-        if (v >= 1) return v > h->hk.ntiles ? h->hk.ntiles : v;
-    }
+    const int v = g_opt_nsplit.load(std::memory_order_relaxed);      // skb_set_option("force_nsplit"): experiments only
+    if (v >= 1) return v > h->hk.ntiles ? h->hk.ntiles : v;
     // Every CTA walks the box table of ALL tiles once to find its queries' exponent references; splitting
     // the tiles over CTAs would repeat that walk per split, and with culling a CTA only visits a fraction
     // of the tiles anyway.  One split also keeps a query's arithmetic a function of the fitted KDE alone.
@@ -176,11 +164,26 @@ struct DevJob {
 };
 
 // All pointers are device pointers here.  grouped: every job scores the same M rows and the
-// finalize step sees all of them; otherwise each job finalizes alone.
-static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupSpec& g, cudaStream_t st)
+// finalize step sees all of them; otherwise each job finalizes alone.  Scratch lives in `ar` (freed on
+// the stream when the caller's Arena goes out of scope, i.e. after everything enqueued here).
+static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupSpec& g, Arena& ar, cudaStream_t st)
 {
     if (n <= 0) return SKB_OK;
     if (n > SKB_MAX_JOBS) return fail(SKB_EINVAL, "too many jobs in one launch (%d > %d)", n, SKB_MAX_JOBS);
+    // ---- validate every job BEFORE anything is enqueued: a bad column index must come back as SKB_EINVAL,
+    //      not as an out-of-bounds read of the ordering kernel ----
+    for (int j = 0; j < n; j++) {
+        const DevJob& dj = jobs[j];
+        const int D = dj.h->hk.D;
+        if (!dj.cols && dj.ldq < D)
+            return fail(SKB_EINVAL, "query has %lld features, the KDE was fitted with %d", dj.ldq, D);
+        for (int k = 0; k < D; k++) {
+            const int c = dj.cols ? dj.cols[k] : k;
+            if (c < 0 || c >= dj.ldq || c > 127)
+                return fail(SKB_EINVAL, "query column index %d out of range for row stride %lld", c, dj.ldq);
+        }
+        if (dj.M > 0x7fffffffLL) return fail(SKB_EINVAL, "too many query rows for one launch");
+    }
     ScoreLaunch L;
     memset(&L, 0, sizeof(L));
     int nsplit[SKB_MAX_JOBS];
@@ -198,8 +201,9 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
         FinJob& fj = L.fin.fj[j];
         const bool need_partial = grouped || nsplit[j] > 1;
         if (need_partial) {
-            SKB_CUDA(dj.h->partial.reserve((size_t)nsplit[j] * (size_t)dj.M * sizeof(double2)));
-            fj.partial = reinterpret_cast<double2*>(dj.h->partial.p);
+            void* p = nullptr;
+            SKB_CUDA(ar.get(&p, (size_t)nsplit[j] * (size_t)dj.M * sizeof(double2)));
+            fj.partial = reinterpret_cast<double2*>(p);
         }
         fj.out_logp = dj.out_logp;
         fj.out_m = dj.out_m;
@@ -228,12 +232,13 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
         for (int j = 0; j < n; j++) {
             if (grouped && j != lead) continue;
             const DevJob& dj = jobs[j];
-            if (dj.M < 1024 || dj.M > 0x7fffffffLL) continue;
+            if (dj.M < 1024) continue;
             const size_t M_ = (size_t)dj.M;
             const size_t tb = sort_temp_bytes(dj.M);
             const size_t need = M_ * (8 + 8 + 4 + 4) + 64 + tb + 256;
-            SKB_CUDA(dj.h->sort_stage.reserve(need));
-            char* base = reinterpret_cast<char*>(dj.h->sort_stage.p);
+            void* blk = nullptr;
+            SKB_CUDA(ar.get(&blk, need));
+            char* base = reinterpret_cast<char*>(blk);
             unsigned long long* keys_in = reinterpret_cast<unsigned long long*>(base);
             unsigned long long* keys_out = keys_in + M_;
             int* idx_in = reinterpret_cast<int*>(keys_out + M_);
@@ -251,11 +256,27 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
     }
     for (int j = 0; j < n; j++) L.fin.fj[j].perm = perm_of[j];
 
+    // arrival counters: zeroed on the call's own stream, every call (the kernels' self-reset is not relied on)
+    auto counters_for = [&](long long M, int** out) -> cudaError_t {
+        const size_t nfb = (size_t)((M + FB - 1) / FB);
+        void* p = nullptr;
+        cudaError_t e = ar.get(&p, nfb * sizeof(int));
+        if (e != cudaSuccess) return e;
+        *out = reinterpret_cast<int*>(p);
+        return cudaMemsetAsync(p, 0, nfb * sizeof(int), st);
+    };
     int* group_counters = nullptr;
-    if (grouped) {
-        const size_t nfb = (size_t)((jobs[0].M + FB - 1) / FB);
-        SKB_CUDA(jobs[0].h->counters.reserve(nfb * sizeof(int), true));
-        group_counters = reinterpret_cast<int*>(jobs[0].h->counters.p);
+    if (grouped) SKB_CUDA(counters_for(jobs[0].M, &group_counters));
+    unsigned long long* stats = nullptr;
+    if (g_opt_stats.load(std::memory_order_relaxed)) {
+        const int dev = jobs[0].h->device;
+        if (dev >= 0 && dev < 64) {
+            if (!g_stats_dev[dev]) {
+                SKB_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_stats_dev[dev]), 4 * sizeof(unsigned long long)));
+                SKB_CUDA(cudaMemset(g_stats_dev[dev], 0, 4 * sizeof(unsigned long long)));
+            }
+            stats = g_stats_dev[dev];
+        }
     }
     // one launch per distinct feature dimension
     bool done[SKB_MAX_JOBS] = {false};
@@ -281,11 +302,10 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
             sj.fin_slot = j;
             sj.cull = cull ? 1 : 0;
             sj.perm = perm_of[j];
+            sj.stats = stats;
             bool ident = true;
             for (int k = 0; k < D; k++) {
                 const int c = dj.cols ? dj.cols[k] : k;
-                if (c < 0 || c >= dj.ldq || c > 127)
-                    return fail(SKB_EINVAL, "query column index %d out of range for row stride %lld", c, dj.ldq);
                 sj.cols[k] = (signed char)c;
                 ident &= (c == k);
             }
@@ -297,9 +317,7 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
             } else {
                 sj.fin_first = j; sj.fin_count = 1;
                 if (nsplit[j] > 1) {
-                    const size_t nfb = (size_t)((dj.M + FB - 1) / FB);
-                    SKB_CUDA(dj.h->counters.reserve(nfb * sizeof(int), true));
-                    sj.counters = reinterpret_cast<int*>(dj.h->counters.p);
+                    SKB_CUDA(counters_for(dj.M, &sj.counters));
                     sj.expected = nsplit[j];
                 }
             }
@@ -307,18 +325,73 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
             if (nsplit[j] > max_split) max_split = nsplit[j];
             if (dj.h->hk.ntiles > max_ntiles) max_ntiles = dj.h->hk.ntiles;
         }
-        // culling off -> the instantiation tuned for all-pairs evaluation (same bits, see skb_internal.h)
-        const bool dense_q = !cull;
-        const int QB = NT * (dense_q ? queries_per_thread_dense(D) : queries_per_thread(D));
-        const long long max_qblocks = (max_rows + QB - 1) / QB;
-        if (max_qblocks > 0x7fffffffLL) return fail(SKB_EINVAL, "too many query rows for one launch");
-        if (max_qblocks > 0) SKB_CUDA(launch_score(D, dense_q, L, nl, max_qblocks, max_split, max_ntiles, st));
+        if (max_rows > 0) SKB_CUDA(launch_score(D, !cull, L, nl, max_rows, max_split, max_ntiles, st));
     }
     return SKB_OK;
 }
 
-// rows per staged chunk when query / output buffers live on the host
+// rows per chunk of a device-resident table (bounds the per-call scratch) and of a host table (copy / compute overlap)
 static const long long STAGE_ROWS = 1LL << 22;
+static const long long HOST_STAGE_ROWS = 1LL << 19;
+
+// Copy / compute overlap for calls whose buffers live in host memory: uploads and downloads run on a private
+// copy stream, ordered against the caller's stream with events (two buffers in flight).
+struct HostStager {
+    cudaStream_t main = nullptr, copy = nullptr;
+    cudaEvent_t up[2] = {nullptr, nullptr}, kd[2] = {nullptr, nullptr}, down[2] = {nullptr, nullptr}, start = nullptr;
+    bool down_pending[2] = {false, false};
+    cudaError_t init(cudaStream_t st)
+    {
+        main = st;
+        cudaError_t e = cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return e;
+        for (int i = 0; i < 2; i++) {
+            if ((e = cudaEventCreateWithFlags(&up[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&kd[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&down[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+        }
+        if ((e = cudaEventCreateWithFlags(&start, cudaEventDisableTiming)) != cudaSuccess) return e;
+        // the copy stream must not run ahead of work already queued on the caller's stream (buffer allocation)
+        if ((e = cudaEventRecord(start, main)) != cudaSuccess) return e;
+        return cudaStreamWaitEvent(copy, start, 0);
+    }
+    cudaError_t upload(void* dst, const void* src, size_t bytes, int b)
+    {
+        cudaError_t e;
+        if (kd[b] && (e = cudaStreamWaitEvent(copy, kd[b], 0)) != cudaSuccess) return e;   // buffer b's last kernels are done
+        if ((e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, copy)) != cudaSuccess) return e;
+        return cudaEventRecord(up[b], copy);
+    }
+    cudaError_t mark_upload(int b) { return cudaEventRecord(up[b], copy); }
+    cudaError_t wait_upload(int b) { return cudaStreamWaitEvent(main, up[b], 0); }
+    cudaError_t wait_download(int b) { return down_pending[b] ? cudaStreamWaitEvent(main, down[b], 0) : cudaSuccess; }
+    cudaError_t kernels_done(int b) { return cudaEventRecord(kd[b], main); }
+    cudaError_t download(void* dst, const void* src, size_t bytes, int b)
+    {
+        cudaError_t e = cudaStreamWaitEvent(copy, kd[b], 0);                                // buffer b's kernels are done
+        if (e != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, copy)) != cudaSuccess) return e;
+        down_pending[b] = true;
+        return cudaEventRecord(down[b], copy);
+    }
+    cudaError_t finish()
+    {
+        cudaError_t e = cudaStreamSynchronize(copy);
+        if (e != cudaSuccess) return e;
+        // scratch of the call is freed on `main`: order it after the copies too, and leave nothing in flight
+        return cudaStreamSynchronize(main);
+    }
+    ~HostStager()
+    {
+        if (copy) { cudaStreamSynchronize(copy); cudaStreamDestroy(copy); }
+        for (int i = 0; i < 2; i++) {
+            if (up[i]) cudaEventDestroy(up[i]);
+            if (kd[i]) cudaEventDestroy(kd[i]);
+            if (down[i]) cudaEventDestroy(down[i]);
+        }
+        if (start) cudaEventDestroy(start);
+    }
+};
 
 }  // namespace skb
 
@@ -380,12 +453,20 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
         }
 
     int rc = SKB_OK;
+    raise_pool_threshold(device);
+    cudaStream_t st = nullptr;              // the fit runs on a private stream and is synchronised before returning
     std::vector<double> wh, cs;
     void* d_train_tmp = nullptr;
     double* d_w = nullptr;
+    int* d_perm = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     auto cleanup = [&](int code) {
+        if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
         if (d_train_tmp) cudaFree(d_train_tmp);
         if (d_w) cudaFree(d_w);
+        if (d_perm) cudaFree(d_perm);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
         if (code != SKB_OK) { skb_destroy(k); }
         return code;
     };
@@ -399,26 +480,28 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
         }                                                                                      \
     } while (0)
 
-    // ---- weights: validate, sum, max, sequential cumsum (host, fp64) ----
+    SKB_CUDA_C(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    // ---- weights: validate, sum, max, sequential cumsum (host, fp64: numpy's own rounding) ----
     double wmax = 1.0;
     hk.sum_w = (double)N;
+    long long nv = N;                       // rows with positive weight
     if (w) {
         wh.resize((size_t)N);
         if (is_device_ptr(w)) SKB_CUDA_C(cudaMemcpy(wh.data(), w, (size_t)N * 8, cudaMemcpyDeviceToHost));
         else memcpy(wh.data(), w, (size_t)N * 8);
         wmax = 0.0;
+        nv = 0;
         for (int64_t i = 0; i < N; i++) {
             const double v = wh[(size_t)i];
             if (!(v >= 0.0) || !std::isfinite(v))
                 return cleanup(fail(SKB_EINVAL, "Negative values in data passed to `sample_weight` (or non-finite) at row %lld",
                                     (long long)i));
             if (v > wmax) wmax = v;
+            nv += (v > 0.0);
         }
         if (!(wmax > 0.0)) return cleanup(fail(SKB_EINVAL, "all sample weights are zero"));
-        // numpy.sum is a pairwise sum; reproduce its 8-lane, 128-block structure closely enough
-        // (differences are O(1e-16) relative and only enter through log(sum_w)).
         {
-            long double acc = 0.0L;
+            long double acc = 0.0L;          // differences to numpy's pairwise sum are O(1e-16) relative and only enter through log(sum_w)
             for (int64_t i = 0; i < N; i++) acc += wh[(size_t)i];
             hk.sum_w = (double)acc;
         }
@@ -433,6 +516,16 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
     }
     hk.log_norm = skb_log_knorm(d, h) - std::log(hk.sum_w) + std::log(wmax);
     k->log_wmax = std::log(wmax);
+    hk.ntiles = (int)((nv + TN - 1) / TN);
+    hk.nsuper = (hk.ntiles + SG - 1) / SG;
+    hk.nchunk = (hk.nsuper + CG - 1) / CG;
+    // reference bias: the exponent window keeps terms down to 2^-(126 - bias) of the reference term, so the
+    // worst-case truncation is N 2^-(126 - bias) relative; 90 up to 4e6 rows, one binade less per doubling beyond
+    {
+        int extra = 0;
+        while (extra < 24 && ((long long)(1 << 22) << extra) < nv) extra++;
+        hk.ref_bias = 90.f - (float)extra;
+    }
 
     // ---- device buffers ----
     SKB_CUDA_C(cudaMalloc(&k->zt64, (size_t)N * d * sizeof(double)));
@@ -442,9 +535,19 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
         SKB_CUDA_C(cudaMalloc(&d_w, (size_t)N * 8));
         SKB_CUDA_C(cudaMemcpy(d_w, wh.data(), (size_t)N * 8, cudaMemcpyHostToDevice));
     }
+    const size_t tile_bytes = (size_t)hk.ntiles * stage_floats(d) * sizeof(float);
+    SKB_CUDA_C(cudaMalloc(&k->tiles, tile_bytes));
+    SKB_CUDA_C(cudaMalloc(&k->boxes, (size_t)hk.ntiles * 2 * d * sizeof(float)));
+    SKB_CUDA_C(cudaMalloc(&k->sboxes, (size_t)(hk.nsuper + hk.nchunk) * 2 * d * sizeof(float)));   // super-boxes, then chunk boxes
+    float* cboxes = k->sboxes + (size_t)hk.nsuper * 2 * d;
+    SKB_CUDA_C(cudaMalloc(&d_perm, (size_t)hk.ntiles * TN * sizeof(int)));
     SKB_CUDA_C(cudaMalloc(&k->dk, sizeof(KdeDev)));
     hk.zt64 = k->zt64;
     hk.cumsum_w = k->cumsum;
+    hk.tiles = k->tiles;
+    hk.boxes = k->boxes;
+    hk.sboxes = k->sboxes;
+    hk.cboxes = cboxes;
     SKB_CUDA_C(cudaMemcpy(k->dk, &hk, sizeof(KdeDev), cudaMemcpyHostToDevice));
 
     const void* d_train = train;
@@ -455,50 +558,19 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
         SKB_CUDA_C(cudaMemcpy(d_train_tmp, train, bytes, cudaMemcpyHostToDevice));
         d_train = d_train_tmp;
     }
-    // whitened fp64 rows (original order: the draw centres)
-    SKB_CUDA_C(launch_fit(d_train, train_dtype == SKB_F32, N, d, ld_train, train_is_whitened, k->dk, k->zt64, 0));
-
-    // ---- kd-tree order of the weighted points: every tile of TN points is one leaf ----
-    {
-        std::vector<double> zh((size_t)N * d);
-        SKB_CUDA_C(cudaMemcpy(zh.data(), k->zt64, zh.size() * 8, cudaMemcpyDeviceToHost));
-        std::vector<float> zf((size_t)N * d);
-        for (size_t i = 0; i < zf.size(); i++) zf[i] = (float)(zh[i] * hk.c);
-        std::vector<double>().swap(zh);
-        std::vector<int> order;
-        order.reserve((size_t)N);
-        for (int64_t i = 0; i < N; i++)
-            if (!w || wh[(size_t)i] > 0.0) order.push_back((int)i);
-        kd_order(zf.data(), d, order.data(), (long long)order.size());
-        hk.ntiles = (int)((order.size() + TN - 1) / TN);
-        for (int kk = 0; kk < d; kk++) { hk.glo[kk] = INFINITY; hk.ghi[kk] = -INFINITY; }
-        for (int idx : order)
-            for (int kk = 0; kk < d; kk++) {
-                const float v = zf[(size_t)idx * d + kk];
-                if (v < hk.glo[kk]) hk.glo[kk] = v;
-                if (v > hk.ghi[kk]) hk.ghi[kk] = v;
-            }
-        order.resize((size_t)hk.ntiles * TN, -1);
-        SKB_CUDA_C(cudaMalloc(&k->perm, order.size() * sizeof(int)));
-        SKB_CUDA_C(cudaMemcpy(k->perm, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
-    }
-    const size_t tile_bytes = (size_t)hk.ntiles * stage_floats(d) * sizeof(float);
-    SKB_CUDA_C(cudaMalloc(&k->tiles, tile_bytes));
-    SKB_CUDA_C(cudaMalloc(&k->boxes, (size_t)hk.ntiles * 2 * d * sizeof(float)));
-    hk.nsuper = (hk.ntiles + SG - 1) / SG;
-    hk.nchunk = (hk.nsuper + CG - 1) / CG;
-    SKB_CUDA_C(cudaMalloc(&k->sboxes, (size_t)(hk.nsuper + hk.nchunk) * 2 * d * sizeof(float)));   // super-boxes, then chunk boxes
-    float* cboxes = k->sboxes + (size_t)hk.nsuper * 2 * d;
-    SKB_CUDA_C(launch_pack(k->zt64, k->perm, d, hk.c, d_w, 1.0 / wmax, k->tiles, hk.ntiles, k->boxes, k->sboxes, cboxes, 0));
-    hk.tiles = k->tiles;
-    hk.boxes = k->boxes;
-    hk.sboxes = k->sboxes;
-    hk.cboxes = cboxes;
-    SKB_CUDA_C(cudaMemcpy(k->dk, &hk, sizeof(KdeDev), cudaMemcpyHostToDevice));
-    SKB_CUDA_C(cudaStreamSynchronize(0));
-    cudaFree(k->perm);
-    k->perm = nullptr;
-    SKB_CUDA_C(k->small.reserve(64, true));
+    // ---- the fit proper, all on the device: whitened fp64 rows (original order: the draw centres) -> kd order of
+    //      the weighted rows (every tile of TN points is one leaf) -> packed tiles + the three box levels ----
+    SKB_CUDA_C(cudaEventCreate(&ev0));
+    SKB_CUDA_C(cudaEventCreate(&ev1));
+    SKB_CUDA_C(cudaEventRecord(ev0, st));
+    SKB_CUDA_C(launch_fit(d_train, train_dtype == SKB_F32, N, d, ld_train, train_is_whitened, k->dk, k->zt64, st));
+    SKB_CUDA_C(launch_kd_order(k->zt64, d_w, N, nv, d, hk.c, d_perm, k->dk, st));     // also fills dk->glo / ghi
+    SKB_CUDA_C(launch_pack(k->zt64, d_perm, d, hk.c, d_w, 1.0 / wmax, k->tiles, hk.ntiles, k->boxes, k->sboxes, cboxes, st));
+    SKB_CUDA_C(cudaEventRecord(ev1, st));
+    SKB_CUDA_C(cudaMemcpyAsync(hk.glo, reinterpret_cast<char*>(k->dk) + offsetof(KdeDev, glo), sizeof(hk.glo) + sizeof(hk.ghi),
+                               cudaMemcpyDeviceToHost, st));
+    SKB_CUDA_C(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&k->fit_ms, ev0, ev1);
 #undef SKB_CUDA_C
     rc = cleanup(SKB_OK);
     *out = k;
@@ -513,12 +585,9 @@ int skb_destroy(skb_handle h)
     if (h->tiles) cudaFree(h->tiles);
     if (h->boxes) cudaFree(h->boxes);
     if (h->sboxes) cudaFree(h->sboxes);
-    if (h->perm) cudaFree(h->perm);
     if (h->zt64) cudaFree(h->zt64);
     if (h->cumsum) cudaFree(h->cumsum);
     if (h->dk) cudaFree(h->dk);
-    h->partial.release(); h->counters.release(); h->q_stage.release(); h->out_stage.release();
-    h->aux_stage.release(); h->flag_stage.release(); h->sort_stage.release(); h->small.release();
     cudaGetLastError();
     delete h;
     return SKB_OK;
@@ -528,6 +597,7 @@ int64_t skb_n_train(skb_handle h) { return h ? h->hk.N : 0; }
 int skb_ndim(skb_handle h) { return h ? h->hk.D : 0; }
 double skb_sum_weight(skb_handle h) { return h ? h->hk.sum_w : 0.0; }
 int skb_device(skb_handle h) { return h ? h->device : -1; }
+double skb_fit_ms(skb_handle h) { return h ? (double)h->fit_ms : 0.0; }
 
 // ---- scoring ------------------------------------------------------------------------------------
 static int check_query_args(skb_handle h, const void* q, int q_dtype, int64_t M, int64_t ldq)
@@ -555,46 +625,77 @@ static int score_one(skb_handle h, const void* q, int q_dtype, int64_t M, int64_
     bool any_host_out = false;
     for (double* o : outs) if (o && !is_device_ptr(o)) any_host_out = true;
     const GroupSpec g;
+    const size_t esz = q_dtype == SKB_F32 ? 4 : 8;
     if (q_dev && !any_host_out) {
-        // device resident: still walk the table in STAGE_ROWS chunks so the partial-state scratch stays bounded
-        const size_t esz_d = q_dtype == SKB_F32 ? 4 : 8;
+        // device resident: still walk the table in STAGE_ROWS chunks so the per-call scratch stays bounded
         for (int64_t a = 0; a < M; a += STAGE_ROWS) {
             const int64_t m = (M - a < STAGE_ROWS) ? (M - a) : STAGE_ROWS;
-            DevJob dj{h, reinterpret_cast<const char*>(q) + (size_t)a * ldq * esz_d, q_dtype == SKB_F32, q_is_whitened,
+            Arena ar(st);
+            DevJob dj{h, reinterpret_cast<const char*>(q) + (size_t)a * ldq * esz, q_dtype == SKB_F32, q_is_whitened,
                       m, ldq, cols, out_logp ? out_logp + a : nullptr, out_m ? out_m + a : nullptr,
                       out_s ? out_s + a : nullptr};
-            rc = run_jobs_device(&dj, 1, false, g, st);
+            rc = run_jobs_device(&dj, 1, false, g, ar, st);
             if (rc) return rc;
         }
         return SKB_OK;
     }
-    // staged path: chunks of rows through device scratch
-    const size_t esz = q_dtype == SKB_F32 ? 4 : 8;
-    for (int64_t a = 0; a < M; a += STAGE_ROWS) {
-        const int64_t m = (M - a < STAGE_ROWS) ? (M - a) : STAGE_ROWS;
+    // staged path: chunks of rows through device scratch, double buffered — the upload of chunk i+1 (copy stream)
+    // overlaps the kernels of chunk i, and the download of chunk i is issued after the kernels of chunk i+1 are
+    // queued, so that a blocking (pageable) download never leaves the GPU without work
+    const int64_t step = M > (1 << 20) ? HOST_STAGE_ROWS : M;
+    const int64_t nchunks = (M + step - 1) / step;
+    void* qbuf[2] = {nullptr, nullptr};
+    double* obuf[2] = {nullptr, nullptr};
+    Arena keep(st);
+    for (int b = 0; b < (nchunks > 1 ? 2 : 1); b++) {
+        if (!q_dev) SKB_CUDA(keep.get(&qbuf[b], (size_t)step * ldq * esz));
+        void* p = nullptr;
+        SKB_CUDA(keep.get(&p, (size_t)step * 8 * 3));
+        obuf[b] = reinterpret_cast<double*>(p);
+    }
+    HostStager hs;                                          // after `keep`: destroyed (and its stream drained) first
+    SKB_CUDA(hs.init(st));
+    auto upload = [&](int64_t c) -> cudaError_t {
+        if (q_dev) return cudaSuccess;
+        const int64_t a = c * step, m = (M - a < step) ? (M - a) : step;
         const char* qsrc = reinterpret_cast<const char*>(q) + (size_t)a * ldq * esz;
-        const void* qd = qsrc;
-        if (!q_dev) {
-            const size_t bytes = ((size_t)(m - 1) * ldq + (cols ? ldq : ldq)) * esz;
-            SKB_CUDA(h->q_stage.reserve(bytes));
-            SKB_CUDA(cudaMemcpyAsync(h->q_stage.p, qsrc, bytes, cudaMemcpyHostToDevice, st));
-            qd = h->q_stage.p;
-        }
-        SKB_CUDA(h->out_stage.reserve((size_t)m * 8 * 3));
+        return hs.upload(qbuf[c & 1], qsrc, (size_t)m * ldq * esz, (int)(c & 1));
+    };
+    auto download = [&](int64_t c) -> cudaError_t {
+        const int64_t a = c * step, m = (M - a < step) ? (M - a) : step;
+        const int b = (int)(c & 1);
+        for (int t = 0; t < 3; t++)
+            if (outs[t] && !is_device_ptr(outs[t])) {
+                cudaError_t e = hs.download(outs[t] + a, obuf[b] + (size_t)t * m, (size_t)m * 8, b);
+                if (e != cudaSuccess) return e;
+            }
+        return cudaSuccess;
+    };
+    SKB_CUDA(upload(0));
+    for (int64_t c = 0; c < nchunks; c++) {
+        const int64_t a = c * step, m = (M - a < step) ? (M - a) : step;
+        const int b = (int)(c & 1);
+        if (c + 1 < nchunks) SKB_CUDA(upload(c + 1));
+        if (!q_dev) SKB_CUDA(hs.wait_upload(b));
+        const void* qd = q_dev ? reinterpret_cast<const char*>(q) + (size_t)a * ldq * esz : qbuf[b];
         double* dst[3];
         for (int t = 0; t < 3; t++) {
             if (!outs[t]) dst[t] = nullptr;
             else if (is_device_ptr(outs[t])) dst[t] = outs[t] + a;
-            else dst[t] = reinterpret_cast<double*>(h->out_stage.p) + (size_t)t * m;
+            else dst[t] = obuf[b] + (size_t)t * m;
         }
-        DevJob dj{h, qd, q_dtype == SKB_F32, q_is_whitened, m, ldq, cols, dst[0], dst[1], dst[2]};
-        rc = run_jobs_device(&dj, 1, false, g, st);
-        if (rc) return rc;
-        for (int t = 0; t < 3; t++)
-            if (outs[t] && !is_device_ptr(outs[t]))
-                SKB_CUDA(cudaMemcpyAsync(outs[t] + a, dst[t], (size_t)m * 8, cudaMemcpyDeviceToHost, st));
-        SKB_CUDA(cudaStreamSynchronize(st));
+        SKB_CUDA(hs.wait_download(b));                     // the previous user of obuf[b] has been copied out
+        {
+            Arena ar(st);
+            DevJob dj{h, qd, q_dtype == SKB_F32, q_is_whitened, m, ldq, cols, dst[0], dst[1], dst[2]};
+            rc = run_jobs_device(&dj, 1, false, g, ar, st);
+            if (rc) return rc;
+        }
+        SKB_CUDA(hs.kernels_done(b));
+        if (c >= 1) SKB_CUDA(download(c - 1));
     }
+    SKB_CUDA(download(nchunks - 1));
+    SKB_CUDA(hs.finish());
     return SKB_OK;
 }
 
@@ -623,8 +724,6 @@ int skb_score_batch(const skb_job* jobs, int n_jobs, void* stream)
         if (rc) return rc;
         if (jobs[j].M > 0 && !jobs[j].out_logp) return fail(SKB_EINVAL, "job %d: NULL output pointer", j);
         if (jobs[j].kde->device != jobs[0].kde->device) return fail(SKB_EINVAL, "jobs of one batch must share a device");
-        for (int k = 0; k < j; k++)
-            if (jobs[k].kde == jobs[j].kde) return fail(SKB_EINVAL, "a KDE handle may appear once per batch");
         if (jobs[j].M > 0 && (!is_device_ptr(jobs[j].q) || !is_device_ptr(jobs[j].out_logp))) all_dev = false;
         if (jobs[j].M > STAGE_ROWS) all_dev = false;        // oversized tables take the chunked single-job path
     }
@@ -646,7 +745,9 @@ int skb_score_batch(const skb_job* jobs, int n_jobs, void* stream)
                          jobs[j].ldq, jobs[j].cols, jobs[j].out_logp, nullptr, nullptr};
     }
     const GroupSpec g;
-    return run_jobs_device(dj, n, false, g, reinterpret_cast<cudaStream_t>(stream));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Arena ar(st);
+    return run_jobs_device(dj, n, false, g, ar, st);
 }
 
 int skb_ratio_accept(const skb_handle* kdes, int n_kde, const int32_t* sign, const double* log_abs_jac,
@@ -660,8 +761,6 @@ int skb_ratio_accept(const skb_handle* kdes, int n_kde, const int32_t* sign, con
         int rc = check_query_args(kdes[k], q, q_dtype, M, ldq);
         if (rc) return rc;
         if (kdes[k]->device != kdes[0]->device) return fail(SKB_EINVAL, "KDEs of one group must share a device");
-        for (int j = 0; j < k; j++)
-            if (kdes[j] == kdes[k]) return fail(SKB_EINVAL, "a KDE handle may appear once per group");
         if (sign[k] != 1 && sign[k] != -1) return fail(SKB_EINVAL, "sign[%d] must be +1 or -1", k);
     }
     if (M == 0) return SKB_OK;
@@ -676,52 +775,99 @@ int skb_ratio_accept(const skb_handle* kdes, int n_kde, const int32_t* sign, con
     const bool ac_dev = !accept || is_device_ptr(accept);
     const bool ib_dev = !in_band || is_device_ptr(in_band);
     const bool all_dev = q_dev && u_dev && lp_dev && lr_dev && ac_dev && ib_dev;
-    const int64_t step = STAGE_ROWS;
-    for (int64_t a = 0; a < M; a += step) {
-        const int64_t m = (M - a < step) ? (M - a) : step;
-        const void* qd = reinterpret_cast<const char*>(q) + (size_t)a * ldq * esz;
-        if (!q_dev) {
-            const size_t bytes = (size_t)m * ldq * esz;
-            SKB_CUDA(h0->q_stage.reserve(bytes));
-            SKB_CUDA(cudaMemcpyAsync(h0->q_stage.p, qd, bytes, cudaMemcpyHostToDevice, st));
-            qd = h0->q_stage.p;
-        }
-        GroupSpec g;
+    auto group_of = [&](GroupSpec& g) {
         g.ratio = 1; g.sign = sign; g.log_abs_jac = log_abs_jac; g.log_m = log_m; g.band = band;
-        // aux staging: [u | log_ratio | logp x n_kde] doubles
-        const size_t aux_doubles = (size_t)m * (2 + (size_t)n_kde);
-        if (!(u_dev && lp_dev && lr_dev)) SKB_CUDA(h0->aux_stage.reserve(aux_doubles * 8));
-        double* aux = reinterpret_cast<double*>(h0->aux_stage.p);
-        if (u) {
-            if (u_dev) g.u = u + a;
-            else { SKB_CUDA(cudaMemcpyAsync(aux, u + a, (size_t)m * 8, cudaMemcpyHostToDevice, st)); g.u = aux; }
+    };
+    if (all_dev) {
+        for (int64_t a = 0; a < M; a += STAGE_ROWS) {
+            const int64_t m = (M - a < STAGE_ROWS) ? (M - a) : STAGE_ROWS;
+            GroupSpec g;
+            group_of(g);
+            g.u = u ? u + a : nullptr;
+            g.out_log_ratio = out_log_ratio ? out_log_ratio + a : nullptr;
+            g.accept = accept ? accept + a : nullptr;
+            g.in_band = in_band ? in_band + a : nullptr;
+            DevJob dj[SKB_MAX_GROUP];
+            for (int k = 0; k < n_kde; k++)
+                dj[k] = DevJob{kdes[k], reinterpret_cast<const char*>(q) + (size_t)a * ldq * esz, q_dtype == SKB_F32, 0, m, ldq,
+                               cols ? cols + (size_t)k * SKB_MAXD : nullptr,
+                               out_logp ? out_logp + (size_t)k * M + a : nullptr, nullptr, nullptr};
+            Arena ar(st);
+            int rc = run_jobs_device(dj, n_kde, true, g, ar, st);
+            if (rc) return rc;
         }
-        if (out_log_ratio) g.out_log_ratio = lr_dev ? out_log_ratio + a : aux + m;
-        if (!(ac_dev && ib_dev)) SKB_CUDA(h0->flag_stage.reserve((size_t)m * 2));
-        unsigned char* fl = reinterpret_cast<unsigned char*>(h0->flag_stage.p);
-        if (accept) g.accept = ac_dev ? accept + a : fl;
-        if (in_band) g.in_band = ib_dev ? in_band + a : fl + m;
+        return SKB_OK;
+    }
+    // host buffers: chunks through device scratch with the copies on a side stream (see score_one)
+    const int64_t step = M > (1 << 20) ? HOST_STAGE_ROWS : M;
+    const int64_t nchunks = (M + step - 1) / step;
+    const int nbuf = nchunks > 1 ? 2 : 1;
+    void* qbuf[2] = {nullptr, nullptr};
+    double* aux[2] = {nullptr, nullptr};      // [u | log_ratio | logp x n_kde] doubles
+    unsigned char* fl[2] = {nullptr, nullptr};   // [accept | in_band]
+    Arena keep(st);
+    for (int b = 0; b < nbuf; b++) {
+        void* p = nullptr;
+        if (!q_dev) SKB_CUDA(keep.get(&qbuf[b], (size_t)step * ldq * esz));
+        SKB_CUDA(keep.get(&p, (size_t)step * (2 + (size_t)n_kde) * 8));
+        aux[b] = reinterpret_cast<double*>(p);
+        SKB_CUDA(keep.get(&p, (size_t)step * 2));
+        fl[b] = reinterpret_cast<unsigned char*>(p);
+    }
+    HostStager hs;
+    SKB_CUDA(hs.init(st));
+    auto upload = [&](int64_t c) -> cudaError_t {
+        const int64_t a = c * step, m = (M - a < step) ? (M - a) : step;
+        const int b = (int)(c & 1);
+        cudaError_t e = cudaSuccess;
+        if (!q_dev) e = hs.upload(qbuf[b], reinterpret_cast<const char*>(q) + (size_t)a * ldq * esz, (size_t)m * ldq * esz, b);
+        if (e == cudaSuccess && u && !u_dev) e = hs.upload(aux[b], u + a, (size_t)m * 8, b);
+        if (e == cudaSuccess) e = hs.mark_upload(b);
+        return e;
+    };
+    auto download = [&](int64_t c) -> cudaError_t {
+        const int64_t a = c * step, m = (M - a < step) ? (M - a) : step;
+        const int b = (int)(c & 1);
+        cudaError_t e = cudaSuccess;
+        if (out_log_ratio && !lr_dev) e = hs.download(out_log_ratio + a, aux[b] + m, (size_t)m * 8, b);
+        if (out_logp && !lp_dev)
+            for (int k = 0; k < n_kde && e == cudaSuccess; k++)
+                e = hs.download(out_logp + (size_t)k * M + a, aux[b] + (size_t)(2 + k) * m, (size_t)m * 8, b);
+        if (e == cudaSuccess && accept && !ac_dev) e = hs.download(accept + a, fl[b], (size_t)m, b);
+        if (e == cudaSuccess && in_band && !ib_dev) e = hs.download(in_band + a, fl[b] + m, (size_t)m, b);
+        return e;
+    };
+    SKB_CUDA(upload(0));
+    for (int64_t c = 0; c < nchunks; c++) {
+        const int64_t a = c * step, m = (M - a < step) ? (M - a) : step;
+        const int b = (int)(c & 1);
+        if (c + 1 < nchunks) SKB_CUDA(upload(c + 1));
+        SKB_CUDA(hs.wait_upload(b));
+        SKB_CUDA(hs.wait_download(b));
+        const void* qd = q_dev ? reinterpret_cast<const char*>(q) + (size_t)a * ldq * esz : qbuf[b];
+        GroupSpec g;
+        group_of(g);
+        if (u) g.u = u_dev ? u + a : aux[b];
+        if (out_log_ratio) g.out_log_ratio = lr_dev ? out_log_ratio + a : aux[b] + m;
+        if (accept) g.accept = ac_dev ? accept + a : fl[b];
+        if (in_band) g.in_band = ib_dev ? in_band + a : fl[b] + m;
         DevJob dj[SKB_MAX_GROUP];
         for (int k = 0; k < n_kde; k++) {
             double* lp = nullptr;
-            if (out_logp) lp = lp_dev ? out_logp + (size_t)k * M + a : aux + (size_t)(2 + k) * m;
+            if (out_logp) lp = lp_dev ? out_logp + (size_t)k * M + a : aux[b] + (size_t)(2 + k) * m;
             dj[k] = DevJob{kdes[k], qd, q_dtype == SKB_F32, 0, m, ldq, cols ? cols + (size_t)k * SKB_MAXD : nullptr,
                            lp, nullptr, nullptr};
         }
-        int rc = run_jobs_device(dj, n_kde, true, g, st);
-        if (rc) return rc;
-        if (!all_dev) {
-            if (out_log_ratio && !lr_dev)
-                SKB_CUDA(cudaMemcpyAsync(out_log_ratio + a, aux + m, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
-            if (out_logp && !lp_dev)
-                for (int k = 0; k < n_kde; k++)
-                    SKB_CUDA(cudaMemcpyAsync(out_logp + (size_t)k * M + a, aux + (size_t)(2 + k) * m, (size_t)m * 8,
-                                             cudaMemcpyDeviceToHost, st));
-            if (accept && !ac_dev) SKB_CUDA(cudaMemcpyAsync(accept + a, fl, (size_t)m, cudaMemcpyDeviceToHost, st));
-            if (in_band && !ib_dev) SKB_CUDA(cudaMemcpyAsync(in_band + a, fl + m, (size_t)m, cudaMemcpyDeviceToHost, st));
-            SKB_CUDA(cudaStreamSynchronize(st));
+        {
+            Arena ar(st);
+            int rc = run_jobs_device(dj, n_kde, true, g, ar, st);
+            if (rc) return rc;
         }
+        SKB_CUDA(hs.kernels_done(b));
+        if (c >= 1) SKB_CUDA(download(c - 1));
     }
+    SKB_CUDA(download(nchunks - 1));
+    SKB_CUDA(hs.finish());
     return SKB_OK;
 }
 
@@ -745,8 +891,14 @@ int skb_draw(skb_handle h, int64_t M, const double* u, const double* z, uint64_t
     bool any_host = false, any_dev = false;
     for (const void* p : ptrs) if (p) { if (is_device_ptr(p)) any_dev = true; else any_host = true; }
     if (any_host && any_dev) return fail(SKB_EINVAL, "skb_draw: mix of host and device buffers is not supported");
-    unsigned long long* d_count = reinterpret_cast<unsigned long long*>(h->small.p);
-    if (n_flagged) SKB_CUDA(cudaMemsetAsync(d_count, 0, 8, st));
+    Arena ar(st);
+    unsigned long long* d_count = nullptr;
+    if (n_flagged) {
+        void* p = nullptr;
+        SKB_CUDA(ar.get(&p, 8));
+        d_count = reinterpret_cast<unsigned long long*>(p);
+        SKB_CUDA(cudaMemsetAsync(d_count, 0, 8, st));
+    }
     if (!any_host) {
         SKB_CUDA(launch_draw(h->dk, D, M, u, z, seed, offset, reinterpret_cast<const long long*>(rows), rcol, rmin,
                              rmax, max_attempts, reinterpret_cast<long long*>(out_idx), out_x, ld_out, out_z, out_flag,
@@ -756,12 +908,15 @@ int skb_draw(skb_handle h, int64_t M, const double* u, const double* z, uint64_t
             // scattered destination rows with host outputs: the caller owns the full arrays, so stage the
             // draws densely and scatter on the host.
         }
+        void* blk = nullptr;
+        {
+            const size_t mmax = (size_t)(M < STAGE_ROWS ? M : STAGE_ROWS);
+            SKB_CUDA(ar.get(&blk, mmax * (2 + 3 * (size_t)D) * 8 + mmax));
+        }
         for (int64_t a = 0; a < M; a += STAGE_ROWS) {
             const int64_t m = (M - a < STAGE_ROWS) ? (M - a) : STAGE_ROWS;
             // layout of the staging block (doubles): u[m] z[m*D] x[m*D] zz[m*D] idx[m] then flags
-            const size_t nd = (size_t)m * (2 + 3 * (size_t)D);
-            SKB_CUDA(h->aux_stage.reserve(nd * 8 + (size_t)m));
-            double* base = reinterpret_cast<double*>(h->aux_stage.p);
+            double* base = reinterpret_cast<double*>(blk);
             double* du = base; double* dz = du + m; double* dx = dz + (size_t)m * D; double* dzz = dx + (size_t)m * D;
             long long* didx = reinterpret_cast<long long*>(dzz + (size_t)m * D);
             unsigned char* dfl = reinterpret_cast<unsigned char*>(didx + m);
@@ -841,14 +996,35 @@ int skb_compact(const uint8_t* flags, int64_t M, const void* rows, int dtype, in
     return SKB_OK;
 }
 
+int skb_set_option(const char* name, int value)
+{
+    if (!name) return fail(SKB_EINVAL, "NULL option name");
+    if (!strcmp(name, "cull")) { g_opt_cull.store(value ? 1 : 0); return SKB_OK; }
+    if (!strcmp(name, "force_nsplit")) { g_opt_nsplit.store(value > 0 ? value : 0); return SKB_OK; }
+    if (!strcmp(name, "stats")) { g_opt_stats.store(value ? 1 : 0); return SKB_OK; }
+    return fail(SKB_EINVAL, "unknown option '%s' (cull, force_nsplit, stats)", name);
+}
+
+int skb_get_option(const char* name)
+{
+    if (!name) return -1;
+    if (!strcmp(name, "cull")) return g_opt_cull.load();
+    if (!strcmp(name, "force_nsplit")) return g_opt_nsplit.load();
+    if (!strcmp(name, "stats")) return g_opt_stats.load();
+    return -1;
+}
+
 int skb_debug_counters(int device, uint64_t* out4, int reset)
 {
     if (!out4) return fail(SKB_EINVAL, "NULL output pointer");
     if (skb_device_count() <= 0) return fail(SKB_ECUDA, "no CUDA device available");
+    for (int i = 0; i < 4; i++) out4[i] = 0;
+    if (device < 0 || device >= 64 || !g_stats_dev[device]) return SKB_OK;      // nothing was counted (skb_set_option("stats", 1) first)
     DeviceGuard guard(device);
     unsigned long long tmp[4];
     SKB_CUDA(cudaDeviceSynchronize());
-    SKB_CUDA(read_stats(tmp, reset));
+    SKB_CUDA(cudaMemcpy(tmp, g_stats_dev[device], sizeof(tmp), cudaMemcpyDeviceToHost));
+    if (reset) SKB_CUDA(cudaMemset(g_stats_dev[device], 0, sizeof(tmp)));
     for (int i = 0; i < 4; i++) out4[i] = tmp[i];
     return SKB_OK;
 }

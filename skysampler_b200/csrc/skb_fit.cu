@@ -12,6 +12,9 @@
 // tiles are skipped with a box test (skb_score.cu) — the result is what the dense evaluation gives.
 #include "skb_internal.h"
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <vector>
 
 namespace skb {
 
@@ -124,6 +127,230 @@ cudaError_t launch_pack(const double* zt64, const int* perm, int D, double c, co
     skb_groupbox_kernel<<<(unsigned)((nchunk * D + 127) / 128), 128, 0, st>>>(sboxes, D, nsuper, CG, nchunk, cboxes);
     count_launch(4);
     return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// kd ordering of the training points ON THE DEVICE (fit time).
+//
+// The tiles of a fitted KDE are the leaves of a kd-tree: recursive median split along the widest
+// coordinate, the left part always a whole number of tiles (of super-boxes / chunks higher up), so that
+// every aligned run of SG tiles / CG super-boxes is a subtree with a tight union box.  The split SIZES
+// depend on the point count only, so the host lays out every level's node table up front and the device
+// runs, per level and without any host synchronisation:
+//   kd_bounds_kernel   per-node bounding boxes (warp-aggregated atomic min / max on order-preserving uints)
+//   kd_key_kernel      widest coordinate per node -> 64-bit key (node id << 32 | ordered coordinate)
+//   CUB radix sort     (key, row id) pairs: every node's rows end up sorted along its split coordinate,
+//                      the first `nl` of them are the left child
+//   kd_relabel_kernel  heap-numbered child ids for the next level
+// ~15 levels x (4 small kernels + one N-pair sort) = a few milliseconds at N = 1e6.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ord_f32(float f)
+{
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float unord_f32(unsigned o)
+{
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+// want_flags: out[i] = (w[i] > 0);  else out[i] = i
+__global__ void kd_init_kernel(const double* __restrict__ w, long long N, int* __restrict__ out, int want_flags)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    out[i] = want_flags ? ((w[i] > 0.0) ? 1 : 0) : (int)i;
+}
+
+__global__ void kd_fill_kernel(int* __restrict__ p, long long n, int v)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// bounds[node][0][k] = ordered min (starts at ~0), bounds[node][1][k] = ordered max (starts at 0)
+__global__ void kd_boundsinit_kernel(unsigned* __restrict__ bounds, long long n, int D)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) bounds[i] = ((i / D) & 1) ? 0u : 0xffffffffu;
+}
+
+__global__ void kd_bounds_kernel(const double* __restrict__ zt64, const int* __restrict__ idx, const int* __restrict__ nodeid,
+                                 long long nv, int D, double c, int base, unsigned* __restrict__ bounds)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = p < nv;
+    const int node = on ? nodeid[p] : -1;
+    const int node0 = __shfl_sync(0xffffffffu, node, 0);
+    const bool uniform = __all_sync(0xffffffffu, node == node0);
+    const double* row = zt64 + (long long)(on ? idx[p] : 0) * D;
+    for (int k = 0; k < D; k++) {
+        const unsigned o = on ? ord_f32((float)(row[k] * c)) : 0u;
+        if (uniform) {                                   // whole warp in one node (top levels): one atomic pair per warp
+            unsigned lo = on ? o : 0xffffffffu, hi = o;
+            for (int s = 16; s > 0; s >>= 1) {
+                lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, s));
+                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, s));
+            }
+            if ((threadIdx.x & 31) == 0 && node0 >= 0) {
+                atomicMin(&bounds[(size_t)(node0 - base) * 2 * D + k], lo);
+                atomicMax(&bounds[(size_t)(node0 - base) * 2 * D + D + k], hi);
+            }
+        } else if (on) {
+            atomicMin(&bounds[(size_t)(node - base) * 2 * D + k], o);
+            atomicMax(&bounds[(size_t)(node - base) * 2 * D + D + k], o);
+        }
+    }
+}
+
+__global__ void kd_key_kernel(const double* __restrict__ zt64, const int* __restrict__ idx, const int* __restrict__ nodeid,
+                              long long nv, int D, double c, int base, const unsigned* __restrict__ bounds,
+                              unsigned long long* __restrict__ keys)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nv) return;
+    const int node = nodeid[p];
+    const unsigned* b = bounds + (size_t)(node - base) * 2 * D;
+    int kbest = 0;
+    float wbest = unord_f32(b[D]) - unord_f32(b[0]);
+    for (int k = 1; k < D; k++) {
+        const float wk = unord_f32(b[D + k]) - unord_f32(b[k]);
+        if (wk > wbest) { wbest = wk; kbest = k; }
+    }
+    const float v = (float)(zt64[(long long)idx[p] * D + kbest] * c);
+    keys[p] = ((unsigned long long)(unsigned)node << 32) | ord_f32(v);
+}
+
+// tbl[(node - base) * 2] = first position of the node, [.. + 1] = rows of its left child
+__global__ void kd_relabel_kernel(const unsigned long long* __restrict__ keys_sorted, long long nv, int base,
+                                  const long long* __restrict__ tbl, int* __restrict__ nodeid)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nv) return;
+    const int node = (int)(keys_sorted[p] >> 32);
+    const long long begin = tbl[(size_t)(node - base) * 2], nl = tbl[(size_t)(node - base) * 2 + 1];
+    nodeid[p] = 2 * node + ((p - begin) >= nl ? 1 : 0);
+}
+
+__global__ void kd_finish_kernel(const int* __restrict__ idx, long long nv, long long npad, int* __restrict__ perm,
+                                 const unsigned* __restrict__ root_bounds, int D, KdeDev* __restrict__ kde)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < npad) perm[p] = p < nv ? idx[p] : -1;
+    if (p < D) {
+        kde->glo[p] = unord_f32(root_bounds[p]);
+        kde->ghi[p] = unord_f32(root_bounds[D + p]);
+    }
+}
+
+// perm [ceil(nv / TN) * TN] <- kd order of the rows with positive weight (all rows when w == NULL), -1 padded;
+// the global box of the packed coordinates is written straight into the device descriptor.  nv = number of
+// such rows (counted by the caller on its host copy of the weights).  Everything is stream-ordered; the only
+// host work is the level table.
+cudaError_t launch_kd_order(const double* zt64, const double* w, long long N, long long nv, int D, double c,
+                            int* perm, KdeDev* kde_dev, cudaStream_t st)
+{
+    const long long TN = tile_points(D);
+    const long long npad = ((nv + TN - 1) / TN) * TN;
+    const int bs = 256;
+    if (nv <= 0 || nv > N || N >= (1LL << 31)) return cudaErrorInvalidValue;
+    // ---- host: node table of every level (sizes depend on nv only) ----
+    struct Node { long long begin, n; int id; };
+    struct Level { size_t tbl_off; int base; int nnodes; bool splits; };
+    std::vector<Node> cur{{0, nv, 1}}, nxt;
+    std::vector<long long> tbl;
+    std::vector<Level> levels;
+    for (int L = 0;; L++) {
+        if (L >= 30) return cudaErrorInvalidValue;               // node ids are 31-bit
+        Level lv{tbl.size(), 1 << L, 1 << L, false};
+        tbl.resize(tbl.size() + 2 * (size_t)lv.nnodes, 0);
+        nxt.clear();
+        for (const Node& nd : cur) {
+            long long nl = nd.n;
+            if (nd.n > TN) {
+                const long long n = nd.n;
+                const long long unit = n > (long long)CG * SG * TN ? (long long)CG * SG * TN
+                                       : (n > (long long)SG * TN ? (long long)SG * TN : TN);
+                const long long nunit = (n + unit - 1) / unit;
+                nl = ((nunit + 1) / 2) * unit;                    // 0 < nl < n because nunit >= 2
+                lv.splits = true;
+                nxt.push_back({nd.begin, nl, 2 * nd.id});
+                nxt.push_back({nd.begin + nl, n - nl, 2 * nd.id + 1});
+            } else {
+                nxt.push_back({nd.begin, nd.n, 2 * nd.id});
+            }
+            tbl[lv.tbl_off + 2 * (size_t)(nd.id - lv.base)] = nd.begin;
+            tbl[lv.tbl_off + 2 * (size_t)(nd.id - lv.base) + 1] = nl;
+        }
+        levels.push_back(lv);
+        if (!lv.splits) break;
+        cur.swap(nxt);
+    }
+    // ---- device scratch from the stream-ordered pool ----
+    size_t sort_bytes = 0, sel_bytes = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const unsigned long long*)nullptr,
+                                                    (unsigned long long*)nullptr, (const int*)nullptr, (int*)nullptr, (int)nv);
+    if (e != cudaSuccess) return e;
+    e = cub::DeviceSelect::Flagged(nullptr, sel_bytes, thrust::counting_iterator<int>(0), (const int*)nullptr, (int*)nullptr,
+                                   (int*)nullptr, (int)N);
+    if (e != cudaSuccess) return e;
+    const size_t tmp_bytes = sort_bytes > sel_bytes ? sort_bytes : sel_bytes;
+    const size_t max_nodes = (size_t)levels.back().nnodes;
+    size_t off = 0;
+    auto carve = [&off](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_keys0 = carve((size_t)nv * 8), o_keys1 = carve((size_t)nv * 8);
+    const size_t o_idx0 = carve((size_t)N * 4), o_idx1 = carve((size_t)N * 4), o_node = carve((size_t)nv * 4);
+    const size_t o_flags = carve((size_t)N * 4), o_cnt = carve(16), o_root = carve(2 * SKB_MAXD * 4);
+    const size_t o_bounds = carve(max_nodes * 2 * D * 4), o_tbl = carve(tbl.size() * 8), o_tmp = carve(tmp_bytes);
+    char* pool = nullptr;
+    if ((e = cudaMallocAsync(reinterpret_cast<void**>(&pool), off, st)) != cudaSuccess) return e;
+    auto done = [&](cudaError_t code) { cudaFreeAsync(pool, st); return code; };
+    unsigned long long* keys0 = reinterpret_cast<unsigned long long*>(pool + o_keys0);
+    unsigned long long* keys1 = reinterpret_cast<unsigned long long*>(pool + o_keys1);
+    int* idx_cur = reinterpret_cast<int*>(pool + o_idx0);
+    int* idx_alt = reinterpret_cast<int*>(pool + o_idx1);
+    int* nodeid = reinterpret_cast<int*>(pool + o_node);
+    int* flags = reinterpret_cast<int*>(pool + o_flags);
+    unsigned* root = reinterpret_cast<unsigned*>(pool + o_root);
+    unsigned* bounds = reinterpret_cast<unsigned*>(pool + o_bounds);
+    long long* dtbl = reinterpret_cast<long long*>(pool + o_tbl);
+    void* tmp = pool + o_tmp;
+    // pageable source: the runtime stages the table before cudaMemcpyAsync returns, so `tbl` may go out of scope
+    if ((e = cudaMemcpyAsync(dtbl, tbl.data(), tbl.size() * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) return done(e);
+    const unsigned gridN = (unsigned)((N + bs - 1) / bs), gridV = (unsigned)((nv + bs - 1) / bs);
+    if (w) {                                             // rows with positive weight, original order
+        kd_init_kernel<<<gridN, bs, 0, st>>>(w, N, flags, 1);
+        size_t tb = tmp_bytes;
+        if ((e = cub::DeviceSelect::Flagged(tmp, tb, thrust::counting_iterator<int>(0), flags, idx_cur,
+                                            reinterpret_cast<int*>(pool + o_cnt), (int)N, st)) != cudaSuccess) return done(e);
+        count_launch(3);
+    } else {
+        kd_init_kernel<<<gridN, bs, 0, st>>>(nullptr, N, idx_cur, 0);
+        count_launch();
+    }
+    kd_fill_kernel<<<gridV, bs, 0, st>>>(nodeid, nv, 1);
+    count_launch();
+    for (size_t L = 0; L < levels.size(); L++) {
+        const Level& lv = levels[L];
+        if (L > 0 && !lv.splits) break;
+        unsigned* b = L == 0 ? root : bounds;            // the root box is kept: it is the KDE's global box
+        const long long nb = (long long)lv.nnodes * 2 * D;
+        kd_boundsinit_kernel<<<(unsigned)((nb + bs - 1) / bs), bs, 0, st>>>(b, nb, D);
+        kd_bounds_kernel<<<gridV, bs, 0, st>>>(zt64, idx_cur, nodeid, nv, D, c, lv.base, b);
+        count_launch(2);
+        if (!lv.splits) break;
+        kd_key_kernel<<<gridV, bs, 0, st>>>(zt64, idx_cur, nodeid, nv, D, c, lv.base, b, keys0);
+        size_t tb = tmp_bytes;
+        if ((e = cub::DeviceRadixSort::SortPairs(tmp, tb, keys0, keys1, idx_cur, idx_alt, (int)nv, 0, 32 + (int)L + 1,
+                                                 st)) != cudaSuccess) return done(e);
+        kd_relabel_kernel<<<gridV, bs, 0, st>>>(keys1, nv, lv.base, dtbl + lv.tbl_off, nodeid);
+        count_launch(6);
+        int* t = idx_cur; idx_cur = idx_alt; idx_alt = t;
+        if ((e = cudaGetLastError()) != cudaSuccess) return done(e);
+    }
+    kd_finish_kernel<<<(unsigned)((npad + bs - 1) / bs), bs, 0, st>>>(idx_cur, nv, npad, perm, root, D, kde_dev);
+    count_launch();
+    return done(cudaGetLastError());
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -107,6 +107,7 @@ struct KdeDev {
     double h;
     double sum_w;
     double log_norm;         // log_knorm - log(sum_w) + log(w_max)   (natural log)
+    float ref_bias;          // the exponent reference sits this many binades below the closest weighted term (90 up to 4e6 rows)
     float glo[SKB_MAXD], ghi[SKB_MAXD];   // bounding box of all packed points (Morton quantisation of queries)
     double mu[SKB_MAXD];
     double Wc[SKB_MAXD * SKB_MAXD];    // forward map prescaled by c:  c*z_k = sum_i (x_i-mu_i) Wc[i*D+k]
@@ -129,6 +130,7 @@ struct ScoreJob {
     int fin_slot;            // this job's index in the FinTable
     int cull;                // 1: skip tiles whose box proves every term flushes to zero
     const int* perm;         // visit order -> row of the query table (Morton order), or NULL
+    unsigned long long* stats;   // 4 diagnostic counters, or NULL (production: nothing is counted)
     signed char cols[SKB_MAXD];
 };
 
@@ -172,7 +174,9 @@ cudaError_t launch_query_order(const KdeDev* kde, const void* q, int q_f32, long
                                int q_is_whitened, const signed char* cols_dev, unsigned long long* keys_in,
                                unsigned long long* keys_out, int* idx_in, int* idx_out, void* temp, size_t temp_bytes,
                                cudaStream_t st);
-cudaError_t launch_score(int D, bool dense_q, const ScoreLaunch& L, int njobs, long long max_qblocks, int max_split,
+cudaError_t launch_kd_order(const double* zt64, const double* w, long long N, long long nv, int D, double c,
+                            int* perm, KdeDev* kde_dev, cudaStream_t st);
+cudaError_t launch_score(int D, bool dense_q, const ScoreLaunch& L, int njobs, long long max_rows, int max_split,
                          int max_ntiles, cudaStream_t st);
 int score_ctas_per_sm(int D, bool dense_q);
 cudaError_t launch_draw(const KdeDev* kde, int D, long long M, const double* u, const double* z,
@@ -185,7 +189,6 @@ cudaError_t launch_compact(const unsigned char* flags, long long M, const void* 
                            unsigned long long* block_counts, unsigned long long* total,
                            cudaStream_t st);
 long long compact_nblocks(long long M);
-cudaError_t read_stats(unsigned long long* out4, int reset);
 cudaError_t measure_pipes(double ms_each, double* fma_lane_per_s, double* ex2_per_s);
 
 void count_launch(int n = 1);

@@ -90,13 +90,11 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// diagnostics (warp level): [0] (query, point) pairs per lane re-run after an exponent-window overflow,
-// [1] (query, point) pairs per lane evaluated (x 32 lanes = pairs evaluated), [2] tiles culled by the box
-// tests, [3] tiles in range
-__device__ unsigned long long g_stats[4];
-
+// diagnostics, only when a launch carries a counter block (ScoreJob::stats; skb_set_option("stats", 1)) — warp level:
+// [0] (query, point) pairs per lane re-run after an exponent-window overflow, [1] (query, point) pairs per lane
+// evaluated (x 32 lanes = pairs evaluated), [2] tiles culled by the box tests, [3] tiles in range
 constexpr float OVERFLOW_LIMIT = 1.329228e36f;    // 2^120: a block partial sum at/above this is re-run
-constexpr float REF_BIAS = 90.f;                  // reference sits this many binades below the closest point seen
+constexpr float LW_CAP = 64.f;                    // a weight lighter than 2^-64 w_max moves the reference by at most this
 constexpr int SUB_MAX = 64;                       // points per overflow-checked block (at most one tile)
 constexpr float CULL_MARGIN = 128.f;              // box lower bound this far past the reference => all terms flush to 0
 
@@ -132,12 +130,10 @@ struct StepOperands {
             xa[k] = pk(v.x, v.y);
             xb[k] = pk(v.z, v.w);
         }
-        if (WITH_W) {
+        {
             const float4 w4 = *reinterpret_cast<const float4*>(tile + D * TN + j);
             wa = pk(w4.x, w4.y);
             wb = pk(w4.z, w4.w);
-        } else {
-            wa = 0; wb = 0;
         }
     }
 };
@@ -215,8 +211,12 @@ __device__ __forceinline__ void step_compute(const StepOperands<D>& op, const fl
         upk(aa, a0, a1);
         upk(ab, b0, b1);
         if (MIN_ONLY) {
-            amin[q] = min3(amin[q], a0, a1);
-            amin[q] = min3(amin[q], b0, b1);
+            // weighted exponents a' = acc - log2 w (rare path: re-centring after an exponent-window overflow)
+            float w0, w1, w2, w3;
+            upk(op.wa, w0, w1);
+            upk(op.wb, w2, w3);
+            amin[q] = min3(amin[q], a0 + fminf(-__log2f(w0), LW_CAP), a1 + fminf(-__log2f(w1), LW_CAP));
+            amin[q] = min3(amin[q], b0 + fminf(-__log2f(w2), LW_CAP), b1 + fminf(-__log2f(w3), LW_CAP));
         } else {
             const u64 ea = pk(ex2_neg(a0), ex2_neg(a1));
             sum2[q] = fma2(op.wa, ea, sum2[q]);
@@ -250,7 +250,7 @@ __device__ __forceinline__ void step_compute8(const float* __restrict__ tile, in
         xa[k] = pk(v.x, v.y); xb[k] = pk(v.z, v.w); xc[k] = pk(u.x, u.y); xd[k] = pk(u.z, u.w);
     }
     u64 wa = 0, wb = 0, wc = 0, wd = 0;
-    if (!MIN_ONLY) {
+    {
         const float4 w4 = *reinterpret_cast<const float4*>(tile + D * TN + j);
         const float4 w5 = *reinterpret_cast<const float4*>(tile + D * TN + j + 4);
         wa = pk(w4.x, w4.y); wb = pk(w4.z, w4.w); wc = pk(w5.x, w5.y); wd = pk(w5.z, w5.w);
@@ -274,10 +274,14 @@ __device__ __forceinline__ void step_compute8(const float* __restrict__ tile, in
         float a0, a1, b0, b1, c0, c1, d0, d1;
         upk(aa, a0, a1); upk(ab, b0, b1); upk(ac, c0, c1); upk(ad, d0, d1);
         if (MIN_ONLY) {
-            amin[q] = min3(amin[q], a0, a1);
-            amin[q] = min3(amin[q], b0, b1);
-            amin[q] = min3(amin[q], c0, c1);
-            amin[q] = min3(amin[q], d0, d1);
+            float w[8];
+            upk(wa, w[0], w[1]); upk(wb, w[2], w[3]); upk(wc, w[4], w[5]); upk(wd, w[6], w[7]);
+#pragma unroll
+            for (int i = 0; i < 8; i++) w[i] = fminf(-__log2f(w[i]), LW_CAP);
+            amin[q] = min3(amin[q], a0 + w[0], a1 + w[1]);
+            amin[q] = min3(amin[q], b0 + w[2], b1 + w[3]);
+            amin[q] = min3(amin[q], c0 + w[4], c1 + w[5]);
+            amin[q] = min3(amin[q], d0 + w[6], d1 + w[7]);
         } else {
             // same accumulation order as two 4-point steps: (a, b) then (c, d)
             sum2[q] = fma2(wa, pk(ex2_neg(a0), ex2_neg(a1)), sum2[q]);
@@ -446,6 +450,33 @@ __device__ __forceinline__ void load_queries(const ScoreJob& job, const KdeDev* 
     }
 }
 
+// min over a tile's points of the WEIGHTED exponent a'_j = |c dz_j|^2 - log2(w_j / w_max)  (the term is 2^-a'), straight
+// from L2.  The window must hang on the largest weighted term: referencing it on the nearest POINT lets a light
+// nearest neighbour push heavy points a little farther out below the flush threshold.  A weight's shift is capped at
+// LW_CAP binades so that no finite weight can move a term past the fp32 exponent range.
+template <int D>
+__device__ __forceinline__ float scan_tile_min(const float* __restrict__ tile, const float (&zq)[D], bool has_w, float best)
+{
+    constexpr int TN = tile_points(D);
+#pragma unroll 1
+    for (int j = 0; j < TN; j += 4) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (has_w) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(tile + D * TN + j));
+            a0 = fminf(-__log2f(w.x), LW_CAP); a1 = fminf(-__log2f(w.y), LW_CAP);
+            a2 = fminf(-__log2f(w.z), LW_CAP); a3 = fminf(-__log2f(w.w), LW_CAP);
+        }
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(tile + k * TN + j));
+            const float d0 = zq[k] - v.x, d1 = zq[k] - v.y, d2 = zq[k] - v.z, d3 = zq[k] - v.w;
+            a0 = fmaf(d0, d0, a0); a1 = fmaf(d1, d1, a1); a2 = fmaf(d2, d2, a2); a3 = fmaf(d3, d3, a3);
+        }
+        best = fminf(best, fminf(fminf(a0, a1), fminf(a2, a3)));
+    }
+    return best;
+}
+
 // Reference exponents, per query and independent of split / batch / GPU:
 //  (1) nearest super-box (SG consecutive kd leaves) by box distance, then the nearest tile box inside
 //      it: the query's "home" tile;
@@ -463,6 +494,8 @@ __device__ __forceinline__ void home_reference(const KdeDev* __restrict__ kde, i
         const float* __restrict__ sbx = kde->sboxes;
         const float* __restrict__ bx = kde->boxes;
         const int nsuper = kde->nsuper;
+        const bool has_w = kde->has_w != 0;
+        const float ref_bias = kde->ref_bias;
         float lbbest[Q];
         int sbest[Q];
 #pragma unroll
@@ -536,17 +569,7 @@ __device__ __forceinline__ void home_reference(const KdeDev* __restrict__ kde, i
             }
             const float* __restrict__ ht = kde->tiles + (size_t)tbest * STAGE_FLOATS;
             float best = INFINITY;
-#pragma unroll 1
-            for (int j = 0; j < TN; j += 4) {
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-                for (int k = 0; k < D; k++) {
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(ht + k * TN + j));
-                    const float d0 = zq[k] - v.x, d1 = zq[k] - v.y, d2 = zq[k] - v.z, d3 = zq[k] - v.w;
-                    a0 = fmaf(d0, d0, a0); a1 = fmaf(d1, d1, a1); a2 = fmaf(d2, d2, a2); a3 = fmaf(d3, d3, a3);
-                }
-                best = fminf(best, fminf(fminf(a0, a1), fminf(a2, a3)));
-            }
+            best = scan_tile_min<D>(ht, zq, has_w, best);
             // D >= 5: the other tiles of the home super-box whose box is closer than the best point so far
 #pragma unroll 1
             for (int t = sbest[q] * SG; SKB_HOME_SUPER && D >= 5 && t < tend; t++) {
@@ -561,21 +584,11 @@ __device__ __forceinline__ void home_reference(const KdeDev* __restrict__ kde, i
                 }
                 if (!(valid && lb < best)) continue;
                 const float* __restrict__ ot = kde->tiles + (size_t)t * STAGE_FLOATS;
-#pragma unroll 1
-                for (int j = 0; j < TN; j += 4) {
-                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-                    for (int k = 0; k < D; k++) {
-                        const float4 v = __ldg(reinterpret_cast<const float4*>(ot + k * TN + j));
-                        const float d0 = zq[k] - v.x, d1 = zq[k] - v.y, d2 = zq[k] - v.z, d3 = zq[k] - v.w;
-                        a0 = fmaf(d0, d0, a0); a1 = fmaf(d1, d1, a1); a2 = fmaf(d2, d2, a2); a3 = fmaf(d3, d3, a3);
-                    }
-                    best = fminf(best, fminf(fminf(a0, a1), fminf(a2, a3)));
-                }
+                best = scan_tile_min<D>(ot, zq, has_w, best);
             }
-            if (!(best < 1.0e30f)) best = REF_BIAS;                   // inf/NaN rows (or padding only): finite reference
+            if (!(best < 1.0e30f)) best = ref_bias;                   // inf/NaN rows (or padding only): finite reference
             bmin[q] = best;
-            const float m = floorf(best) - REF_BIAS;
+            const float m = floorf(best) - ref_bias;
             mref[q] = m;
             nm2[q] = -m;
         }
@@ -682,7 +695,6 @@ constexpr int PQ_ROW = 32;                        // part[query][lane ^ query]: 
 #ifndef SKB_PQ_SLACK
 #define SKB_PQ_SLACK 3        // a lane term >= 2^(SLACK - REF_BIAS) (a point that much closer than the reference) recentres
 #endif
-constexpr float PQ_LIMIT = 8.0779357e-28f * (float)(1u << SKB_PQ_SLACK);   // 2^(SLACK - 90)
 static_assert(PQ_CH <= 32 && PQ_CAP <= 256 && SG == 16, "PQ chunk layout");
 __host__ __device__ constexpr bool pq_mode(int D, int Q) { return SKB_PQ && D >= SKB_PQ_MIN_D && Q == 1 && tile_points(D) == 64; }
 __host__ __device__ constexpr int pq_qstride(int D) { return (D + 4) & ~3; }          // floats per query row: z[0..D), -m, padding to 16 B
@@ -790,7 +802,8 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
     const int lane = tid & 31;
     unsigned n_rerun = 0, n_blocks = 0, n_culled = 0, n_visited = 0;
 
-    float bmin[Q];          // running estimate of the smallest acc seen (absolute)
+    float bmin[Q];          // running estimate of the smallest weighted exponent seen (absolute)
+    const float ref_bias = kde->ref_bias;
     home_reference<D, Q>(kde, ntiles, q2, bmin, mref, nm2);
 
     // ---- which tiles does this CTA need at all?  A tile that every warp can already cull with its initial
@@ -967,7 +980,7 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
 #pragma unroll
                 for (int q = 0; q < Q; q++) {
                     if (!(ts[q] < OVERFLOW_LIMIT)) {
-                        const float delta = floorf(amin[q]) - REF_BIAS;   // new reference relative to mref
+                        const float delta = floorf(amin[q]) - ref_bias;   // new reference relative to mref
                         if (delta < 0.f && delta > -1.0e30f) {
                             fixable = true;
                             bmin[q] = fminf(bmin[q], mref[q] + floorf(amin[q]));
@@ -992,7 +1005,7 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
         // S is rescaled by a power of two); a tighter reference culls more of the tiles still to come
 #pragma unroll
         for (int q = 0; q < Q; q++) {
-            const float want = floorf(bmin[q]) - REF_BIAS;
+            const float want = floorf(bmin[q]) - ref_bias;
             if (mref[q] - want >= 8.f) {
                 S[q] = ldexp(S[q], (int)fmaxf(want - mref[q], -4000.f));
                 mref[q] = want;
@@ -1003,11 +1016,11 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
         if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
 
-    if (lane == 0) {
-        if (n_rerun) atomicAdd(&g_stats[0], (unsigned long long)n_rerun * Q * SUB);
-        atomicAdd(&g_stats[1], (unsigned long long)n_blocks * Q * SUB);
-        atomicAdd(&g_stats[2], (unsigned long long)(n_culled + (unsigned)ntl - n_visited));
-        atomicAdd(&g_stats[3], (unsigned long long)ntl);      // tiles of the split (culled = box-culled at either level)
+    if (job.stats && lane == 0) {
+        if (n_rerun) atomicAdd(&job.stats[0], (unsigned long long)n_rerun * Q * SUB);
+        atomicAdd(&job.stats[1], (unsigned long long)n_blocks * Q * SUB);
+        atomicAdd(&job.stats[2], (unsigned long long)(n_culled + (unsigned)ntl - n_visited));
+        atomicAdd(&job.stats[3], (unsigned long long)ntl);      // tiles of the split (culled = box-culled at either level)
     }
 
     finish_queries<D, Q>(L, job, qbase, tid, M, mref, S, s_last);
@@ -1061,6 +1074,8 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
     double S[Q];
     float nm2[Q];
     mref[0] = 0.f; S[0] = 0.0; nm2[0] = 0.f;
+    const float ref_bias = kde->ref_bias;
+    const float PQ_LIMIT = exp2f((float)SKB_PQ_SLACK - ref_bias);     // a lane term this large re-centres
     home_reference<D, Q>(kde, ntiles, q2, bmin, mref, nm2);
 
 #pragma unroll
@@ -1222,10 +1237,10 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
             // rare: a point >= 8 binades closer than the reference was built for (or a NaN row) — fold the
             // row, move the query's reference to the tile's closest point, re-evaluate
             auto recentre = [&](int i, float a0, float a1) -> float {
-                float am = fminf(a0, a1);
+                float am = fminf(a0 + fminf(-__log2f(w0), LW_CAP), a1 + fminf(-__log2f(w1), LW_CAP));   // weighted exponents
 #pragma unroll
                 for (int off = 16; off >= 1; off >>= 1) am = fminf(am, __shfl_xor_sync(FULL, am, off));
-                const float delta = floorf(am) - REF_BIAS;
+                const float delta = floorf(am) - ref_bias;
                 n_rerun++;
                 if (delta < 0.f && delta > -1.0e30f) {
                     __syncwarp();
@@ -1282,20 +1297,21 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
     __syncwarp();
     S[0] += pq_fold_row(part, lane);
 
-    if (lane == 0) {
-        if (n_rerun) atomicAdd(&g_stats[0], (unsigned long long)n_rerun * 2);
-        atomicAdd(&g_stats[1], n_pairs);
-        atomicAdd(&g_stats[2], (unsigned long long)((unsigned)(t1 - t0) - n_visited));
-        atomicAdd(&g_stats[3], (unsigned long long)(t1 - t0));
+    if (job.stats && lane == 0) {
+        if (n_rerun) atomicAdd(&job.stats[0], (unsigned long long)n_rerun * 2);
+        atomicAdd(&job.stats[1], n_pairs);
+        atomicAdd(&job.stats[2], (unsigned long long)((unsigned)(t1 - t0) - n_visited));
+        atomicAdd(&job.stats[3], (unsigned long long)(t1 - t0));
     }
     finish_queries<D, Q>(L, job, qbase, lane, M, mref, S, s_last);
 }
 
 template <int D, int Q>
-static cudaError_t launch_score_dq(const ScoreLaunch& L, int njobs, long long max_qblocks, int max_split,
+static cudaError_t launch_score_dq(const ScoreLaunch& L, int njobs, long long max_rows, int max_split,
                                    int max_ntiles, cudaStream_t st)
 {
-    dim3 grid((unsigned)max_qblocks, (unsigned)njobs, (unsigned)max_split);
+    constexpr int QB = pq_mode(D, Q) ? 32 : NT * Q;
+    dim3 grid((unsigned)((max_rows + QB - 1) / QB), (unsigned)njobs, (unsigned)max_split);
     if constexpr (pq_mode(D, Q)) {
         const size_t smem = pq_smem_bytes(D);
         cudaError_t e = cudaFuncSetAttribute(skb_score_pq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1311,16 +1327,6 @@ static cudaError_t launch_score_dq(const ScoreLaunch& L, int njobs, long long ma
     }
     count_launch();
     return cudaGetLastError();
-}
-
-cudaError_t read_stats(unsigned long long* out4, int reset)
-{
-    cudaError_t e = cudaMemcpyFromSymbol(out4, g_stats, sizeof(unsigned long long) * 4);
-    if (e == cudaSuccess && reset) {
-        unsigned long long z[4] = {0, 0, 0, 0};
-        e = cudaMemcpyToSymbol(g_stats, z, sizeof(z));
-    }
-    return e;
 }
 
 template <int D, int Q>
@@ -1364,12 +1370,12 @@ int score_ctas_per_sm(int D, bool dense_q)
 
 static_assert(sizeof(ScoreLaunch) <= 4000, "ScoreLaunch must fit the classic 4 KB kernel-parameter space");
 
-cudaError_t launch_score(int D, bool dense_q, const ScoreLaunch& L, int njobs, long long max_qblocks, int max_split,
+cudaError_t launch_score(int D, bool dense_q, const ScoreLaunch& L, int njobs, long long max_rows, int max_split,
                          int max_ntiles, cudaStream_t st)
 {
     switch (D) {
-#define SKB_CASE(d) case d: return dense_q ? launch_score_dq<d, queries_per_thread_dense(d)>(L, njobs, max_qblocks, max_split, max_ntiles, st) \
-                                           : launch_score_dq<d, queries_per_thread(d)>(L, njobs, max_qblocks, max_split, max_ntiles, st);
+#define SKB_CASE(d) case d: return dense_q ? launch_score_dq<d, queries_per_thread_dense(d)>(L, njobs, max_rows, max_split, max_ntiles, st) \
+                                           : launch_score_dq<d, queries_per_thread(d)>(L, njobs, max_rows, max_split, max_ntiles, st);
         SKB_CASE(1) SKB_CASE(2) SKB_CASE(3) SKB_CASE(4) SKB_CASE(5) SKB_CASE(6) SKB_CASE(7) SKB_CASE(8)
         SKB_CASE(9) SKB_CASE(10) SKB_CASE(11) SKB_CASE(12) SKB_CASE(13) SKB_CASE(14) SKB_CASE(15) SKB_CASE(16)
 #undef SKB_CASE

@@ -99,6 +99,7 @@ class GaussianKDE(object):
         self._h = h
         self.n_train_, self.ndim_, self.device_ = n, d, int(dev)
         self.sum_weight_ = float(lib.skb_sum_weight(h))
+        self.fit_ms_ = float(lib.skb_fit_ms(h))           # device time of the fit (whitening, kd ordering, packing)
         return self
 
     def close(self):
@@ -129,7 +130,7 @@ class GaussianKDE(object):
         m, ld = X.shape
         if cols is None and ld != self.ndim_:
             raise ValueError("X has %d features, but GaussianKDE is expecting %d features as input." % (ld, self.ndim_))
-        cols_a = cols_array(cols, self.ndim_)
+        cols_a = cols_array(cols, self.ndim_, ld)
         if _cabi._is_torch(X) and X.is_cuda:
             import torch
             if out is None:
@@ -151,7 +152,7 @@ class GaussianKDE(object):
         h = self._handle()
         X = _as_matrix(X)
         m, ld = X.shape
-        cols_a = cols_array(cols, self.ndim_)
+        cols_a = cols_array(cols, self.ndim_, ld)
         if _cabi._is_torch(X) and X.is_cuda:
             import torch
             om = torch.empty(m, dtype=torch.float64, device=X.device)
@@ -185,6 +186,16 @@ class GaussianKDE(object):
                                    self.ndim_, ptr(out_z), None, None, None))
         res = out_x if raw else out_z
         return (res, idx) if return_index else res
+
+    def draw_streams(self, u, z, out_x, out_z, rows=None, out_idx=None):
+        """Draws from caller-supplied streams (``u`` [n] uniforms, ``z`` [n, d] normals), consumed exactly as
+        sklearn does (_kde.py:338-349): draw i lands in row ``rows[i]`` (default i) of ``out_x`` (raw space)
+        and ``out_z`` (whitened space) — the building block of ``KDEContainer.random_draw``'s redraw loop
+        (emulator.py:371-375)."""
+        h = self._handle()
+        n = len(u)
+        check(_cabi.lib().skb_draw(h, n, ptr(u), ptr(z), 0, 0, ptr(rows), -1, 0.0, 0.0, 1, ptr(out_idx), ptr(out_x),
+                                   self.ndim_, ptr(out_z), None, None, None))
 
     def sample_philox(self, n_samples, seed, offset=0, rcol=-1, rmin=0.0, rmax=0.0, max_attempts=1000,
                       device_out=False, stream=None):
@@ -363,6 +374,8 @@ class KDEContainer(object):
     def construct_kde(self, bandwidth):
         """emulator.py:351-356: fit = upload (whitened rows, weights, whitening maps)."""
         self.bandwidth = bandwidth
+        if getattr(self, "kde", None) is not None:          # re-fit (calc_scores does, chunk after chunk): free the old device copy now
+            self.kde.close()
         self.kde = GaussianKDE(bandwidth=self.bandwidth, kernel=self._kernel, atol=self._atol, rtol=self._rtol,
                                breadth_first=self._breadth_first, device=self._device)
         self.kde.fit(np.asarray(self._data), sample_weight=np.asarray(self.weights, dtype=np.float64),
@@ -391,15 +404,12 @@ class KDEContainer(object):
             raise ValueError("unknown _rng_mode %r" % (self._rng_mode,))
         # stream-for-stream replay of the reference: n uniforms then n*d normals per sample() call,
         # redraw calls consume n_bad then n_bad*d (emulator.py:371-375).
-        lib = _cabi.lib()
-        h = self.kde._handle()
         d = self.ndim
         _res = np.empty((num, d), dtype=np.float64)
         xraw = np.empty((num, d), dtype=np.float64)
         u = self.rng.uniform(0, 1, size=num)
         z = self.rng.normal(0.0, 1.0, size=(num, d))
-        check(lib.skb_draw(h, num, ptr(u), ptr(z), 0, 0, None, -1, 0.0, 0.0, 1, None, ptr(xraw), d, ptr(_res),
-                           None, None, None))
+        self.kde.draw_streams(u, z, xraw, _res)
         if windowed:
             inds = (xraw[:, icol] > rmax) | (xraw[:, icol] < rmin)
             while inds.sum():
@@ -407,8 +417,7 @@ class KDEContainer(object):
                 nb = len(rows)
                 u = self.rng.uniform(0, 1, size=nb)
                 z = self.rng.normal(0.0, 1.0, size=(nb, d))
-                check(lib.skb_draw(h, nb, ptr(u), ptr(z), 0, 0, ptr(rows), -1, 0.0, 0.0, 1, None, ptr(xraw), d,
-                                   ptr(_res), None, None, None))
+                self.kde.draw_streams(u, z, xraw, _res, rows=rows)
                 inds = (xraw[:, icol] > rmax) | (xraw[:, icol] < rmin)
         self._res = _res
         self.res = pd.DataFrame(xraw, columns=self.columns)

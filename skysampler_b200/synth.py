@@ -25,6 +25,24 @@ def mixture(d, n, seed, k=8, cov_scale=1.0, sample_seed=None):
     return np.ascontiguousarray(x)
 
 
+def mixture_big(d, n, seed, k=8, cov_scale=1.0):
+    """The same mixture family as ``mixture`` for multi-million-row sets: rows are generated component by
+    component (no [n, d, d] temporary) and then shuffled, so memory stays at a few copies of [n, d]."""
+    rng = np.random.RandomState(seed)
+    means = rng.normal(0.0, 2.0, size=(k, d))
+    mats = np.eye(d)[None, :, :] + 0.3 * rng.normal(size=(k, d, d))
+    pis = rng.dirichlet(np.ones(k))
+    counts = rng.multinomial(n, pis)
+    x = np.empty((n, d))
+    a = 0
+    for c in range(k):
+        z = rng.normal(size=(counts[c], d))
+        x[a:a + counts[c]] = means[c] + (z @ mats[c].T) * np.sqrt(cov_scale)
+        a += counts[c]
+    rng.shuffle(x)
+    return x
+
+
 def wide_weights(n, seed, nblocks=100):
     """'wide' weights: U(0.5, 2) per 1% block of rows (mimics indexer.py:925 x emulator.py:198)."""
     rng = np.random.RandomState(seed)

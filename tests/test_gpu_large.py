@@ -1,0 +1,104 @@
+"""Parity at BASELINE.json's LARGE training-set sizes and on the exponent window's worst case, through the C ABI.
+
+* config 4 shape (16-D, 2e6 training rows) and the top of config 5 (8-D, 4e6 rows) against the fp64 brute-force
+  oracle (its C twin, oracle/brute64.c, pinned to the numpy one by tests/test_oracle.py) on 2 000 rows each:
+  90 % KDE draws (bulk) + 10 % inflated x2 (tail).  Bar: |d log p| <= 1e-4 within 100 nats of the peak.
+* the adversarial truncation case: the kernels keep pair terms within ~36 binades of the query's reference term;
+  referencing that window on the nearest POINT would drop a heavy shell just outside it when the nearest
+  neighbour is light.  The window hangs on the largest WEIGHTED term, so these cases must stay inside 1e-4.
+"""
+import numpy as np
+import pytest
+
+from oracle import cbrute
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _big_case(d, n, h, seed, weighted):
+    from skysampler_b200 import GaussianKDE, synth
+    x = synth.mixture_big(d, n, seed)
+    w = synth.wide_weights(n, seed + 1) if weighted else None
+    m1, pm, comps, std2 = synth.whiten_params(x[::7], None if w is None else w[::7])     # whitening from a subsample
+    z = np.ascontiguousarray((x - m1) @ comps.T / std2)
+    del x
+    q = synth.queries(z, h, 2000, seed + 2, tail_frac=0.1, tail_scale=2.0)
+    kde = GaussianKDE(h).fit(z, sample_weight=w)
+    got = kde.score_samples(q)
+    fit_ms = kde.fit_ms_
+    again = kde.score_samples(q[500:1500])
+    kde.close()
+    assert np.array_equal(again, got[500:1500])                  # batching invariance at full size
+    ref = cbrute.score(z, w, h, q)
+    near = ref >= ref.max() - 100.0
+    assert near.sum() >= 1500
+    err = np.abs(got - ref)
+    assert err[near].max() <= TOL, (d, n, float(err[near].max()))
+    far = ~near & np.isfinite(ref)
+    if far.any():
+        assert np.all(np.isfinite(got[far])) and (err[far] / np.abs(ref[far])).max() <= 1e-5
+    return float(err[near].max()), fit_ms
+
+
+def test_config4_shape_16d_2e6_rows():
+    err, fit_ms = _big_case(16, 2000000, 0.3, 401, weighted=False)
+    print("d=16 N=2e6: max |dlogp| %.2e, device fit %.1f ms" % (err, fit_ms))
+
+
+def test_config5_top_8d_4e6_rows_weighted():
+    err, fit_ms = _big_case(8, 4000000, 0.1, 522, weighted=True)
+    print("d=8 N=4e6: max |dlogp| %.2e, device fit %.1f ms" % (err, fit_ms))
+
+
+def _shell(rs, n, d, r_lo, r_hi):
+    v = rs.normal(size=(n, d))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    return v * rs.uniform(r_lo, r_hi, size=(n, 1))
+
+
+@pytest.mark.parametrize("d", [1, 2, 4, 6, 8])
+@pytest.mark.parametrize("n_light", [1, 4000])
+def test_light_nearest_neighbour_does_not_truncate_a_heavy_shell(d, n_light):
+    """Nearest neighbour(s) with weight 1e-6 w_max at the query, 3e5 unit-weight points on a shell whose terms are
+    2^-37 .. 2^-40 of an unweighted nearest term: the shell carries most of the density there."""
+    from skysampler_b200 import GaussianKDE
+    rs = np.random.RandomState(100 + d)
+    h = 0.1
+    c2 = np.log2(np.e) / (2 * h * h)                       # term = 2^-(c2 |dz|^2)
+    n_shell = 300000
+    shell = _shell(rs, n_shell, d, np.sqrt(37.0 / c2), np.sqrt(40.0 / c2))
+    light = 1e-3 * h * rs.normal(size=(n_light, d))
+    far = 30.0 + rs.normal(size=(20000, d))                # an unrelated far cluster so that the tree has other leaves
+    z = np.vstack([light, shell, far])
+    w = np.concatenate([np.full(n_light, 1e-6), np.ones(n_shell), np.ones(len(far))])
+    perm = rs.permutation(len(z))
+    z, w = np.ascontiguousarray(z[perm]), np.ascontiguousarray(w[perm])
+    q = np.vstack([np.zeros((1, d)), 0.02 * h * rs.normal(size=(199, d)), 0.5 * h * rs.normal(size=(200, d))])
+    kde = GaussianKDE(h).fit(z, sample_weight=w)
+    got = kde.score_samples(q)
+    kde.close()
+    ref = cbrute.score(z, w, h, q)
+    assert np.all(np.isfinite(got))
+    # the shell matters: dropping it would cost more than a nat at the centre when a single light point sits there
+    if n_light == 1:
+        only_light = np.log(1e-6) - np.log(w.sum()) + (-0.5 * d * np.log(2 * np.pi) - d * np.log(h))
+        assert ref[0] - only_light > 1.0
+    assert np.abs(got - ref).max() <= TOL, float(np.abs(got - ref).max())
+
+
+def test_multi_gpu_sharding_on_nccl():
+    """tools/check_multigpu.py under torchrun on 2 GPUs: query-sharded == single GPU bit for bit, training-sharded
+    partial-LSE combine == full-set score (skipped below 2 GPUs; the gloo twin runs in the CPU suite)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(root, "tools", "check_multigpu.py")]
+    out = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "bit-identical: True" in out.stdout

@@ -249,10 +249,6 @@ def test_pipelined_host_batches_equal_resident_steps():
     ka.close(); kb.close()
 
 
-@pytest.mark.xfail(strict=False, reason="round-1 open item: in a mixed group (6-D + 2-D + 1-D) one member's log p was not bit-identical "
-                   "to its single-KDE call (parity fine).  Suspected cause, fixed after the last GPU run of the round and so "
-                   "unconfirmed: at d=1 the polynomial-exp terms of far points were 2^-125 instead of exactly 0, which made a "
-                   "query's sum depend on the culled tiles its warp companions keep alive (DESIGN.md section 7)")
 def test_fused_ratio_accept_mixes_both_score_kernels():
     """A KDE group with a 6-D member (per-query-culling kernel) and 2-D / 1-D members (lanes = queries kernel):
     the launches share the visit order and the arrival counters; whichever CTA arrives last finalises."""

@@ -155,3 +155,21 @@ def test_fp32_window_model_meets_the_parity_bar_and_culling_is_exact():
         assert np.abs(got - ref)[near].max() <= 1e-4, (d, np.abs(got - ref)[near].max())
         far = ~near
         assert (np.abs(got - ref)[far] / np.abs(ref[far])).max() <= 1e-5
+
+
+def test_c_brute_force_twin_matches_the_numpy_oracle():
+    """oracle/brute64.c (used at the multi-million-row configs) is the same function as oracle/brute64.py."""
+    from oracle import cbrute
+    rs = np.random.RandomState(3)
+    for d, n, h, weighted in ((1, 3000, 0.05, True), (4, 5000, 0.1, True), (8, 4000, 0.1, False), (16, 3000, 0.3, True)):
+        z = rs.normal(size=(n, d))
+        w = rs.uniform(0.5, 2.0, n) if weighted else None
+        if weighted:
+            w[::11] = 0.0
+        q = np.vstack([1.5 * rs.normal(size=(300, d)), 40.0 * rs.normal(size=(20, d))])
+        a = brute64.score(z, w, h, q)
+        b = cbrute.score(z, w, h, q)
+        assert np.all(np.isfinite(b)) and np.abs(a - b).max() <= 1e-9 * max(1.0, np.abs(a).max())
+        ma, sa = brute64.partial_lse(z, w, h, q)
+        mb, sb = cbrute.partial_lse(z, w, h, q)
+        assert np.array_equal(ma, mb) and np.allclose(sa, sb, rtol=1e-12, atol=0)

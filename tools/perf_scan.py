@@ -4,6 +4,7 @@ sys.path.insert(0, ".")
 import numpy as np, torch
 from skysampler_b200 import GaussianKDE, _cabi
 lib = _cabi.lib()
+_cabi.set_option("stats", 1)
 fma, ex2 = C.c_double(), C.c_double()
 lib.skb_measure_pipes(0, 100.0, C.byref(fma), C.byref(ex2))
 dims = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [1, 2, 3, 4, 6, 8, 12, 16]
@@ -31,6 +32,8 @@ for d in dims:
     rate = n * m / ms * 1e3
     peak = min(fma.value / (2 * d + 1), ex2.value)
     st = (C.c_uint64 * 4)(); lib.skb_debug_counters(0, st, 1)
-    print("%s d=%2d N=%d M=%d %8.2f ms  %.3e pairs/s  frac=%.3f  rerun=%.4f  culled=%.3f" % (
-        os.path.basename(_cabi.LIB_PATH), d, n, m, ms, rate, rate / peak, st[0] / max(st[1], 1), st[2] / max(st[3], 1)), flush=True)
+    exec_pairs = st[1] * 32.0 / 4          # 4 launches since the last reset
+    print("%s d=%2d N=%d M=%d %8.2f ms  %.3e pairs/s  frac_alg=%.3f  exec_frac=%.4f  frac_exec=%.3f  culled=%.3f  fit=%.1f ms" % (
+        os.path.basename(_cabi.LIB_PATH), d, n, m, ms, rate, rate / peak, exec_pairs / (float(n) * m),
+        exec_pairs / (ms * 1e-3) / peak, st[2] / max(st[3], 1), kde.fit_ms_), flush=True)
     kde.close()
