@@ -60,7 +60,7 @@ def _shell(rs, n, d, r_lo, r_hi):
 @pytest.mark.parametrize("d", [1, 2, 4, 6, 8])
 @pytest.mark.parametrize("n_light", [1, 4000])
 def test_light_nearest_neighbour_does_not_truncate_a_heavy_shell(d, n_light):
-    """Nearest neighbour(s) with weight 1e-6 w_max at the query, 3e5 unit-weight points on a shell whose terms are
+    """Nearest neighbour(s) with weight 1e-7 w_max at the query, 3e5 unit-weight points on a shell whose terms are
     2^-37 .. 2^-40 of an unweighted nearest term: the shell carries most of the density there."""
     from skysampler_b200 import GaussianKDE
     rs = np.random.RandomState(100 + d)
@@ -71,7 +71,7 @@ def test_light_nearest_neighbour_does_not_truncate_a_heavy_shell(d, n_light):
     light = 1e-3 * h * rs.normal(size=(n_light, d))
     far = 30.0 + rs.normal(size=(20000, d))                # an unrelated far cluster so that the tree has other leaves
     z = np.vstack([light, shell, far])
-    w = np.concatenate([np.full(n_light, 1e-6), np.ones(n_shell), np.ones(len(far))])
+    w = np.concatenate([np.full(n_light, 1e-7), np.ones(n_shell), np.ones(len(far))])
     perm = rs.permutation(len(z))
     z, w = np.ascontiguousarray(z[perm]), np.ascontiguousarray(w[perm])
     q = np.vstack([np.zeros((1, d)), 0.02 * h * rs.normal(size=(199, d)), 0.5 * h * rs.normal(size=(200, d))])
@@ -82,7 +82,7 @@ def test_light_nearest_neighbour_does_not_truncate_a_heavy_shell(d, n_light):
     assert np.all(np.isfinite(got))
     # the shell matters: dropping it would cost more than a nat at the centre when a single light point sits there
     if n_light == 1:
-        only_light = np.log(1e-6) - np.log(w.sum()) + (-0.5 * d * np.log(2 * np.pi) - d * np.log(h))
+        only_light = np.log(1e-7) - np.log(w.sum()) + (-0.5 * d * np.log(2 * np.pi) - d * np.log(h))
         assert ref[0] - only_light > 1.0
     assert np.abs(got - ref).max() <= TOL, float(np.abs(got - ref).max())
 
