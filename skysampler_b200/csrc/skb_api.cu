@@ -89,6 +89,7 @@ static int env_int(const char* name, int dflt)
 static std::atomic<int> g_opt_cull{env_int("SKB_NO_CULL", 0) ? 0 : 1};
 static std::atomic<int> g_opt_nsplit{env_int("SKB_FORCE_NSPLIT", 0)};
 static std::atomic<int> g_opt_stats{0};
+static std::atomic<int> g_opt_kernel{env_int("SKB_KERNEL", 0)};     // 0: work-item-per-lane kernel; 1: round-1 culled kernels (A/B runs)
 static unsigned long long* g_stats_dev[64] = {nullptr};
 
 }  // namespace skb
@@ -325,7 +326,12 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
             if (nsplit[j] > max_split) max_split = nsplit[j];
             if (dj.h->hk.ntiles > max_ntiles) max_ntiles = dj.h->hk.ntiles;
         }
-        if (max_rows > 0) SKB_CUDA(launch_score(D, !cull, L, nl, max_rows, max_split, max_ntiles, st));
+        if (max_rows > 0) {
+            if (cull && g_opt_kernel.load(std::memory_order_relaxed) == 0)
+                SKB_CUDA(launch_score_wil(D, L, nl, max_rows, max_split, st));
+            else
+                SKB_CUDA(launch_score(D, !cull, L, nl, max_rows, max_split, max_ntiles, st));
+        }
     }
     return SKB_OK;
 }
@@ -1002,6 +1008,7 @@ int skb_set_option(const char* name, int value)
     if (!strcmp(name, "cull")) { g_opt_cull.store(value ? 1 : 0); return SKB_OK; }
     if (!strcmp(name, "force_nsplit")) { g_opt_nsplit.store(value > 0 ? value : 0); return SKB_OK; }
     if (!strcmp(name, "stats")) { g_opt_stats.store(value ? 1 : 0); return SKB_OK; }
+    if (!strcmp(name, "kernel")) { g_opt_kernel.store(value); return SKB_OK; }
     return fail(SKB_EINVAL, "unknown option '%s' (cull, force_nsplit, stats)", name);
 }
 
@@ -1011,6 +1018,7 @@ int skb_get_option(const char* name)
     if (!strcmp(name, "cull")) return g_opt_cull.load();
     if (!strcmp(name, "force_nsplit")) return g_opt_nsplit.load();
     if (!strcmp(name, "stats")) return g_opt_stats.load();
+    if (!strcmp(name, "kernel")) return g_opt_kernel.load();
     return -1;
 }
 

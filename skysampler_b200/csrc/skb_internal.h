@@ -176,6 +176,7 @@ cudaError_t launch_query_order(const KdeDev* kde, const void* q, int q_f32, long
                                cudaStream_t st);
 cudaError_t launch_kd_order(const double* zt64, const double* w, long long N, long long nv, int D, double c,
                             int* perm, KdeDev* kde_dev, cudaStream_t st);
+cudaError_t launch_score_wil(int D, const ScoreLaunch& L, int njobs, long long max_rows, int max_split, cudaStream_t st);
 cudaError_t launch_score(int D, bool dense_q, const ScoreLaunch& L, int njobs, long long max_rows, int max_split,
                          int max_ntiles, cudaStream_t st);
 int score_ctas_per_sm(int D, bool dense_q);

@@ -520,6 +520,7 @@ __device__ __forceinline__ void home_reference(const KdeDev* __restrict__ kde, i
         }
 #pragma unroll
         for (int q = 0; q < Q; q++) {
+            if (!alive) { bmin[q] = ref_bias; mref[q] = 0.f; nm2[q] = 0.f; continue; }
             float zq[D];
 #pragma unroll
             for (int k = 0; k < D; k++) zq[k] = q2[q][k];
