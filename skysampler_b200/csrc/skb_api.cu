@@ -53,13 +53,13 @@ static bool is_device_ptr(const void* p)
 // pool (release threshold raised at first use) hands the same blocks back call after call.
 struct Arena {
     cudaStream_t st;
-    void* blocks[24];
+    void* blocks[128];
     int n = 0;
     explicit Arena(cudaStream_t s) : st(s) {}
     cudaError_t get(void** out, size_t bytes)
     {
         *out = nullptr;
-        if (n >= 24) return cudaErrorMemoryAllocation;
+        if (n >= 128) return cudaErrorMemoryAllocation;
         cudaError_t e = cudaMallocAsync(out, bytes ? bytes : 16, st);
         if (e == cudaSuccess) blocks[n++] = *out;
         return e;
@@ -196,11 +196,13 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
         nsplit[j] = plan_nsplit(dj.h, dj.M, same);
         expected_group += nsplit[j];
     }
+    const bool cull = cull_enabled();
+    const bool sparse = cull && g_opt_kernel.load(std::memory_order_relaxed) == 0;   // plan -> bucket -> evaluate -> finalize
     // finalize table
     for (int j = 0; j < n; j++) {
         const DevJob& dj = jobs[j];
         FinJob& fj = L.fin.fj[j];
-        const bool need_partial = grouped || nsplit[j] > 1;
+        const bool need_partial = !sparse && (grouped || nsplit[j] > 1);
         if (need_partial) {
             void* p = nullptr;
             SKB_CUDA(ar.get(&p, (size_t)nsplit[j] * (size_t)dj.M * sizeof(double2)));
@@ -224,7 +226,6 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
     L.fin.in_band = g.in_band;
 
     // ---- visit order of the query rows: Morton order in the prescaled space of the widest KDE ----
-    const bool cull = cull_enabled();
     const int* perm_of[SKB_MAX_JOBS];
     for (int j = 0; j < n; j++) perm_of[j] = nullptr;
     if (cull) {
@@ -267,7 +268,7 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
         return cudaMemsetAsync(p, 0, nfb * sizeof(int), st);
     };
     int* group_counters = nullptr;
-    if (grouped) SKB_CUDA(counters_for(jobs[0].M, &group_counters));
+    if (grouped && !sparse) SKB_CUDA(counters_for(jobs[0].M, &group_counters));
     unsigned long long* stats = nullptr;
     if (g_opt_stats.load(std::memory_order_relaxed)) {
         const int dev = jobs[0].h->device;
@@ -278,6 +279,43 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
             }
             stats = g_stats_dev[dev];
         }
+    }
+    // ---- culled path: per-job query rows + accumulators, one entry list per dimension group ----
+    SparseLaunch SLh;
+    SparseLaunch* SLd_all = nullptr;              // device copies, one per (dimension group, sub-chunk)
+    int n_sl = 0, sl_cap = 0;
+    if (sparse) {
+        SKB_CUDA(sparse_prepare());
+        memset(&SLh, 0, sizeof(SLh));
+        for (int j = 0; j < n; j++) {
+            const DevJob& dj = jobs[j];
+            const int D = dj.h->hk.D;
+            const int qs = (D + 4) & ~3;
+            void* p = nullptr;
+            SKB_CUDA(ar.get(&p, (size_t)dj.M * qs * sizeof(float)));
+            SLh.sj[j].qz = reinterpret_cast<float*>(p);
+            SKB_CUDA(ar.get(&p, (size_t)dj.M * 16));
+            SKB_CUDA(cudaMemsetAsync(p, 0, (size_t)dj.M * 16, st));
+            SLh.sj[j].acc = reinterpret_cast<unsigned long long*>(p);
+            SLh.sj[j].tiles = dj.h->tiles;
+            SLh.sj[j].M = dj.M;
+            SLh.sj[j].qs = qs;
+            SLh.sj[j].D = D;
+        }
+        void* p = nullptr;
+        SKB_CUDA(ar.get(&p, 64));
+        SKB_CUDA(cudaMemsetAsync(p, 0, 64, st));
+        SLh.counter = reinterpret_cast<unsigned long long*>(p);
+        SLh.overflow = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(p) + 16);
+        SLh.stats = stats;
+        // worst-case number of device descriptors: one per sub-chunk per dimension group (bounded below)
+        sl_cap = 0;
+        long long maxM = 0;
+        for (int j = 0; j < n; j++) if (jobs[j].M > maxM) maxM = jobs[j].M;
+        sl_cap = (int)(n * ((maxM + 32 * 128 - 1) / (32 * 128)) + n + 1);
+        if (sl_cap > 4096) sl_cap = 4096;
+        SKB_CUDA(ar.get(&p, (size_t)sl_cap * sizeof(SparseLaunch)));
+        SLd_all = reinterpret_cast<SparseLaunch*>(p);
     }
     // one launch per distinct feature dimension
     bool done[SKB_MAX_JOBS] = {false};
@@ -326,12 +364,61 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
             if (nsplit[j] > max_split) max_split = nsplit[j];
             if (dj.h->hk.ntiles > max_ntiles) max_ntiles = dj.h->hk.ntiles;
         }
-        if (max_rows > 0) {
-            if (cull && g_opt_kernel.load(std::memory_order_relaxed) == 0)
-                SKB_CUDA(launch_score_wil(D, L, nl, max_rows, max_split, st));
-            else
-                SKB_CUDA(launch_score(D, !cull, L, nl, max_rows, max_split, max_ntiles, st));
+        if (max_rows <= 0) continue;
+        if (!sparse) {
+            SKB_CUDA(launch_score(D, !cull, L, nl, max_rows, max_split, max_ntiles, st));
+            continue;
         }
+        // ---- this dimension group's entry list: worst-case-safe capacity, query rows planned in sub-chunks ----
+        SLh.njobs = nl;
+        int nbuckets = 0;
+        double per_warp = 0.0;                       // entries one query warp can reserve over all jobs of the group
+        for (int i = 0; i < nl; i++) {
+            const int slot = L.jobs[i].fin_slot;
+            SLh.jobs_of_group[i] = slot;
+            SLh.sj[slot].tile_base = nbuckets;
+            nbuckets += jobs[slot].h->hk.ntiles;
+            per_warp += 1.14 * jobs[slot].h->hk.ntiles + 2.0 * 256;
+        }
+        const double kCapEntries = 134217728.0;      // 2^27 entries (3.2 GB of scratch with the sorted copy) per sub-chunk
+        long long sub_warps = (long long)(kCapEntries / per_warp);
+        if (sub_warps < 128) sub_warps = 128;
+        const long long all_warps = (max_rows + 31) / 32;
+        if (sub_warps > all_warps) sub_warps = all_warps;
+        const unsigned long long cap = (unsigned long long)((double)(sub_warps + 1) * per_warp) + 1024;
+        if (cap > 0xfff00000ull) return fail(SKB_ENOMEM, "training set too large for one entry list (%d tiles): shard it over GPUs", nbuckets);
+        {
+            void* p = nullptr;
+            SKB_CUDA(ar.get(&p, (size_t)cap * 4 * 6));
+            unsigned* base = reinterpret_cast<unsigned*>(p);
+            SLh.ent_tile = base; SLh.ent_warp = base + cap; SLh.ent_mask = base + 2 * cap;
+            SLh.srt_tile = base + 3 * cap; SLh.srt_warp = base + 4 * cap; SLh.srt_mask = base + 5 * cap;
+            SLh.cap = cap;
+            const int nbp = nbuckets < 49152 ? nbuckets : 49152;
+            SKB_CUDA(ar.get(&p, ((size_t)nbp * 128 + 1) * 4));
+            SLh.hist = reinterpret_cast<unsigned*>(p);
+        }
+        const size_t scan_bytes = sparse_scan_temp_bytes();
+        void* scan_tmp = nullptr;
+        SKB_CUDA(ar.get(&scan_tmp, scan_bytes));
+        for (long long w0 = 0; w0 < all_warps; w0 += sub_warps) {
+            if (n_sl >= sl_cap) return fail(SKB_ENOMEM, "too many planning sub-chunks");
+            SLh.vbeg = w0 * 32;
+            SLh.vend = (w0 + sub_warps) * 32 < max_rows ? (w0 + sub_warps) * 32 : max_rows;
+            SparseLaunch* SLd = SLd_all + n_sl++;
+            SKB_CUDA(cudaMemcpyAsync(SLd, &SLh, sizeof(SparseLaunch), cudaMemcpyHostToDevice, st));   // pageable source: staged before return
+            SKB_CUDA(cudaMemsetAsync(SLh.counter, 0, 8, st));
+            SKB_CUDA(launch_sparse_group(D, L, nl, SLh, SLd, SLh.vend - SLh.vbeg, nbuckets, scan_tmp, scan_bytes,
+                                         jobs[j0].h->sms, st));
+        }
+    }
+    if (sparse) {
+        if (n_sl == 0) return SKB_OK;
+        long long maxM = 0;
+        for (int j = 0; j < n; j++) if (jobs[j].M > maxM) maxM = jobs[j].M;
+        // the last descriptor carries every job's rows / accumulators: finalize all jobs from it
+        if (grouped) SKB_CUDA(launch_sparse_finalize(L, SLd_all + (n_sl - 1), 0, n, 1, jobs[0].M, st));
+        else SKB_CUDA(launch_sparse_finalize(L, SLd_all + (n_sl - 1), 0, 1, n, maxM, st));
     }
     return SKB_OK;
 }

@@ -164,6 +164,35 @@ struct ScoreLaunch {
     FinTable fin;
 };
 
+// ---- the culled score path (skb_sparse.cu): plan -> bucket -> evaluate -> finalize ----
+struct SparseJob {
+    const float* tiles;          // the KDE's tile array
+    float* qz;                   // [M][qs] prescaled whitened query rows: z[0..D), -m, padding
+    unsigned long long* acc;     // [M][2] 128-bit fixed-point sums (lo, hi), LSB 2^-128 relative to 2^m
+    long long M;
+    int tile_base;               // first bucket of this job within its dimension group
+    int qs;
+    int D;
+};
+
+struct SparseLaunch {
+    SparseJob sj[SKB_MAX_JOBS];          // indexed by the job's slot in the finalize table
+    int jobs_of_group[SKB_MAX_JOBS];     // slots of this dimension group's jobs, by increasing tile_base
+    int njobs;                           // jobs in this dimension group
+    unsigned* ent_tile;                  // [cap] entries as emitted: bucket (tile_base + tile), query warp, mask of its queries
+    unsigned* ent_warp;
+    unsigned* ent_mask;
+    unsigned* srt_tile;                  // [cap] the same, sorted by bucket
+    unsigned* srt_warp;
+    unsigned* srt_mask;
+    unsigned long long* counter;         // entries reserved so far
+    unsigned* overflow;                  // set if the entry list ever overflowed (results are then NaN)
+    unsigned* hist;                      // [buckets of a pass][NB_CTAS] (+1): histogram, scanned in place
+    unsigned long long* stats;           // diagnostic counters or NULL
+    unsigned long long cap;
+    long long vbeg, vend;                // visit positions planned by this launch
+};
+
 // kernels / launchers (defined in the .cu files)
 cudaError_t launch_fit(const void* train, int f32, long long N, int D, long long ld, int is_whitened,
                        const KdeDev* kde_dev, double* zt64, cudaStream_t st);
@@ -176,7 +205,12 @@ cudaError_t launch_query_order(const KdeDev* kde, const void* q, int q_f32, long
                                cudaStream_t st);
 cudaError_t launch_kd_order(const double* zt64, const double* w, long long N, long long nv, int D, double c,
                             int* perm, KdeDev* kde_dev, cudaStream_t st);
-cudaError_t launch_score_wil(int D, const ScoreLaunch& L, int njobs, long long max_rows, int max_split, cudaStream_t st);
+size_t sparse_scan_temp_bytes();
+cudaError_t sparse_prepare();
+cudaError_t launch_sparse_group(int D, const ScoreLaunch& L, int nl, const SparseLaunch& SLh, const SparseLaunch* SLd,
+                                long long max_rows, int nbuckets, void* scan_tmp, size_t scan_tmp_bytes, int sms, cudaStream_t st);
+cudaError_t launch_sparse_finalize(const ScoreLaunch& L, const SparseLaunch* SLd, int first, int count, int njobs_y,
+                                   long long max_rows, cudaStream_t st);
 cudaError_t launch_score(int D, bool dense_q, const ScoreLaunch& L, int njobs, long long max_rows, int max_split,
                          int max_ntiles, cudaStream_t st);
 int score_ctas_per_sm(int D, bool dense_q);

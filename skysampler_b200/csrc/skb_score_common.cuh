@@ -341,17 +341,18 @@ __device__ __forceinline__ double final_logp(double log_norm, double S, double m
     return __dadd_rn(__dadd_rn(log_norm, log(S)), -__dmul_rn(m, LN2));
 }
 
-__device__ __forceinline__ void finalize_query(const FinTable& fin, int first, int count,
-                                               long long M, long long v)
+// get(f, v, mstar, S): the (m, S) state of job f for the query at visit position v
+template <class Get>
+__device__ __forceinline__ void finalize_query_with(const FinTable& fin, int first, int count, long long v, Get get)
 {
-    // v: visit-order position (partials);  r: row of the query table (outputs, uniforms)
+    // v: visit-order position (states);  r: row of the query table (outputs, uniforms)
     const int* perm = fin.fj[first].perm;
     const long long r = perm ? perm[v] : v;
     double log_ratio = -fin.log_m;
     for (int f = first; f < first + count; f++) {
         const FinJob& fj = fin.fj[f];
         double mstar, S;
-        merge_partials(fj.partial, fj.nsplit, M, v, mstar, S);
+        get(f, v, mstar, S);
         if (fj.out_m) { fj.out_m[r] = fj.log_wmax - mstar * LN2; fj.out_s[r] = S; }
         const double lp = final_logp(fj.log_norm, S, mstar);
         if (fj.out_logp) fj.out_logp[r] = lp;
@@ -365,6 +366,14 @@ __device__ __forceinline__ void finalize_query(const FinTable& fin, int first, i
             if (fin.in_band) fin.in_band[r] = (fabs(log_ratio - lu) <= fin.band) ? 1 : 0;
         }
     }
+}
+
+__device__ __forceinline__ void finalize_query(const FinTable& fin, int first, int count,
+                                               long long M, long long v)
+{
+    finalize_query_with(fin, first, count, v, [&](int f, long long vv, double& mstar, double& S) {
+        merge_partials(fin.fj[f].partial, fin.fj[f].nsplit, M, vv, mstar, S);
+    });
 }
 
 // ---- load this thread's Q query rows, whiten + prescale in fp64, pack as {z, z} ----

@@ -1,0 +1,618 @@
+// The culled score path for sm_100a: plan -> bucket -> evaluate -> finalize.
+//
+// What the path needs.  A query's log-density is carried by the training tiles (kd leaves) whose bounding box lies within
+// ~38 binades of its largest weighted term; in 8-D that is ~1.3 % of the leaves, and DIFFERENT leaves for different
+// queries — 2^20 queries in 8-D are sparse: even 256 Morton neighbours span more than the kernel radius, so any grouping
+// of queries (a warp, a CTA) needs a tile for only ~10 % of its members.  The all-pairs kernel (skb_score.cu: lanes =
+// queries, tile words broadcast from shared memory) runs the pair arithmetic at 0.82 of the FP32-pipe roofline but evaluates
+// a tile for every query of the warp; round 1's per-query kernel evaluated only needed (query, tile) pairs but with lanes =
+// two training points (query rows re-read, shared-memory partial sums, per-tile ring traffic): 0.30 of the roofline; a
+// CTA-level work-list kernel (profiles/r02d_*) filled its lanes only half and sat on barriers.  So the incidence is
+// sorted GLOBALLY, by tile:
+//
+//   plan      one warp per 32 queries of the visit order: fused fp64 whitening, exponent reference (home super-box scan;
+//             queries far from everything run an exact, warp-cooperative branch and bound), then per chunk of 256 tiles the
+//             chunk-box / super-box tests with one query per lane and the tile tests with one TILE per lane -> entries
+//             (tile, query warp, 32-bit mask of the warp's queries that need the tile), appended to a global list
+//   bucket    counting sort of the entries by tile (per-CTA shared-memory histograms, one scan, scatter)
+//   evaluate  a warp takes 64 consecutive sorted entries (almost always one tile), stages the tile in shared memory and
+//             runs the all-pairs inner loop — 4 points per step, packed FADD2/FFMA2 + MUFU.EX2, tile words broadcast —
+//             with TWO needing queries per lane; every lane is busy and nothing but the needed pairs is evaluated.  A
+//             (query, tile) sum is added to the query's 128-bit FIXED-POINT accumulator with integer atomics: exact and
+//             order independent, so the result is a function of the query and the fitted KDE alone (any batching /
+//             sharding gives the same bits) although the evaluation order is not
+//   finalize  accumulators -> fp64 (m, S) -> log p, ratio and accept test
+//
+// The exponent reference is fixed per query before the first tile: after the plan step every point satisfies
+// |c dz|^2 - log2 w >= best - FAR_LIMIT, so no term exceeds 2^(FAR_LIMIT - bias) and the fixed-point range is never left.
+#include "skb_score_common.cuh"
+#include <cub/device/device_scan.cuh>
+
+namespace skb {
+
+constexpr float FAR_LIMIT = 64.f;                 // references farther than this from every home point are refined exactly
+constexpr int PLAN_WARPS = 4;                     // warps per CTA of the plan kernel (independent of each other)
+constexpr int ENTRY_BLOCK = 256;                  // entries a plan warp reserves at a time (one global atomic per block)
+constexpr int EVAL_EB = 64;                       // sorted entries per evaluate work unit (two per lane)
+constexpr int EVAL_WARPS = 8;
+constexpr int NB_CTAS = 128;                      // CTAs of the bucket kernels (slices of the entry list)
+constexpr int MAX_BUCKETS = 48 * 1024;            // tiles per bucket pass (shared-memory histogram)
+constexpr float FX_SCALE = 18446744073709551616.f;   // 2^64
+
+__host__ __device__ constexpr int sp_qstride(int D) { return (D + 4) & ~3; }                  // z[0..D), -m, padding to 16 B
+__host__ __device__ constexpr int sp_tile_floats(int D) { return (D + 1) * tile_points(D); }  // coordinates + weights
+
+// position of the n-th (0-based) set bit of w; n < popc(w)
+__device__ __forceinline__ int nth_set_bit(unsigned w, unsigned n)
+{
+    int pos = 0;
+    unsigned c = __popc(w & 0xffffu);
+    if (n >= c) { n -= c; pos = 16; w >>= 16; }
+    c = __popc(w & 0xffu);
+    if (n >= c) { n -= c; pos += 8; w >>= 8; }
+    c = __popc(w & 0xfu);
+    if (n >= c) { n -= c; pos += 4; w >>= 4; }
+    c = __popc(w & 0x3u);
+    if (n >= c) { n -= c; pos += 2; w >>= 2; }
+    if (n >= (w & 1u)) pos += 1;
+    return pos;
+}
+
+template <int D>
+__device__ __forceinline__ float box_lb(const float* __restrict__ b, const float (&zq)[D])
+{
+    float lb = 0.f;
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        const float lo = __ldg(b + k), hi = __ldg(b + D + k);
+        const float gap = fmaxf(fmaxf(lo - zq[k], zq[k] - hi), 0.f);      // empty boxes are (inf, -inf): gap = inf
+        lb = fmaf(gap, gap, lb);
+    }
+    return lb;
+}
+
+// min over a tile of the weighted exponent |c dz|^2 - log2 w, lanes = points (warp cooperative, warp-uniform result)
+template <int D>
+__device__ __forceinline__ float coop_scan_tile(const float* __restrict__ tile, const float (&zq)[D], bool has_w, int lane)
+{
+    constexpr int TN = tile_points(D);
+    float b = INFINITY;
+#pragma unroll
+    for (int p = lane; p < TN; p += 32) {
+        float a = has_w ? fminf(-__log2f(__ldg(tile + D * TN + p)), LW_CAP) : 0.f;
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            const float d = zq[k] - __ldg(tile + k * TN + p);
+            a = fmaf(d, d, a);
+        }
+        b = fminf(b, a);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b = fminf(b, __shfl_xor_sync(0xffffffffu, b, o));
+    return b;
+}
+
+// Exact branch and bound for ONE query (broadcast to the warp) whose home estimate `best` is far from everything: every
+// tile whose box comes closer than best - slack is scanned.  Lanes = boxes at each level.  Afterwards every point has
+// |c dz|^2 >= best - slack.
+template <int D>
+__device__ __forceinline__ float coop_refine_reference(const KdeDev* __restrict__ kde, int ntiles, const float (&zq)[D],
+                                                       float best, float slack, int lane)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    const bool has_w = kde->has_w != 0;
+    const int nchunk = kde->nchunk, nsuper = kde->nsuper;
+#pragma unroll 1
+    for (int c0 = 0; c0 < nchunk; c0 += 32) {
+        const int c = c0 + lane;
+        const float lbc = c < nchunk ? box_lb<D>(kde->cboxes + (size_t)c * 2 * D, zq) : INFINITY;
+        unsigned cm = __ballot_sync(FULL, lbc < best - slack);
+        while (cm) {
+            const int cc = c0 + __ffs(cm) - 1;
+            cm &= cm - 1u;
+            const int s = cc * CG + (lane & 15);
+            const float lbs = (lane < CG && s < nsuper) ? box_lb<D>(kde->sboxes + (size_t)s * 2 * D, zq) : INFINITY;
+            unsigned sm = __ballot_sync(FULL, lbs < best - slack);
+            while (sm) {
+                const int ss = cc * CG + __ffs(sm) - 1;
+                sm &= sm - 1u;
+                const int t = ss * SG + (lane & 15);
+                const float lbt = (lane < SG && t < ntiles) ? box_lb<D>(kde->boxes + (size_t)t * 2 * D, zq) : INFINITY;
+                unsigned tm = __ballot_sync(FULL, lbt < best - slack);
+                while (tm) {
+                    const int tt = ss * SG + __ffs(tm) - 1;
+                    tm &= tm - 1u;
+                    best = fminf(best, coop_scan_tile<D>(kde->tiles + (size_t)tt * stage_floats(D), zq, has_w, lane));
+                }
+            }
+        }
+    }
+    return best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(32 * PLAN_WARPS)
+skb_plan_kernel(const __grid_constant__ ScoreLaunch L, const SparseLaunch* __restrict__ SLp)
+{
+    constexpr int QS = sp_qstride(D);
+    constexpr unsigned FULL = 0xffffffffu;
+    __shared__ __align__(16) float rows_s[PLAN_WARPS][32 * QS];
+
+    const ScoreJob& job = L.jobs[blockIdx.y];
+    const SparseLaunch& SL = *SLp;
+    const SparseJob& sj = SL.sj[job.fin_slot];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long M = job.M;
+    const long long vend = SL.vend < M ? SL.vend : M;
+    const long long wbase = SL.vbeg + ((long long)blockIdx.x * PLAN_WARPS + wid) * 32;
+    if (wbase >= vend) return;                              // warps are independent: no CTA barrier below
+    float* rows = rows_s[wid];
+
+    const KdeDev* __restrict__ kde = job.kde;
+    const int ntiles = kde->ntiles;
+    const float ref_bias = kde->ref_bias;
+
+    // ---- this lane's query: whitening, exponent reference ----
+    bool alive = wbase + lane < vend;
+    float q2[1][D];
+    load_queries<D, 1>(job, kde, wbase, lane, M, q2);
+    bool isnan_row = false;
+#pragma unroll
+    for (int k = 0; k < D; k++) isnan_row |= (q2[0][k] != q2[0][k]);
+    float mref[1], bmin[1], nm2[1];
+    home_reference<D, 1>(kde, ntiles, q2, bmin, mref, nm2, alive && !isnan_row);
+    {
+        unsigned farm = __ballot_sync(FULL, alive && !isnan_row && bmin[0] > FAR_LIMIT);
+        while (farm) {
+            const int src = __ffs(farm) - 1;
+            farm &= farm - 1u;
+            float zq[D];
+#pragma unroll
+            for (int k = 0; k < D; k++) zq[k] = __shfl_sync(FULL, q2[0][k], src);
+            float best = __shfl_sync(FULL, bmin[0], src);
+            best = coop_refine_reference<D>(kde, ntiles, zq, best, FAR_LIMIT, lane);
+            if (lane == src && best < bmin[0]) { bmin[0] = best; mref[0] = floorf(best) - ref_bias; }
+        }
+    }
+    // rows past the end of the table and NaN rows need nothing (a NaN row's -m is NaN: finalize propagates it)
+    const float negm = !alive ? INFINITY : (isnan_row ? NAN : -mref[0]);
+    alive = alive && !isnan_row;
+#pragma unroll
+    for (int k = 0; k < D; k++) rows[lane * QS + k] = q2[0][k];
+    rows[lane * QS + D] = negm;
+#pragma unroll
+    for (int k = D + 1; k < QS; k++) rows[lane * QS + k] = 0.f;
+    __syncwarp();
+    if (wbase + lane < vend) {
+        float4* dst = reinterpret_cast<float4*>(sj.qz + (size_t)(wbase + lane) * QS);
+        const float4* src = reinterpret_cast<const float4*>(rows + lane * QS);
+#pragma unroll
+        for (int k = 0; k < QS / 4; k++) dst[k] = src[k];
+    }
+
+    // ---- entries: (tile, this warp, mask of its queries that need the tile) ----
+    const unsigned my_warp = (unsigned)(wbase >> 5);
+    const unsigned bucket0 = (unsigned)sj.tile_base;
+    unsigned ebase = 0xffffffffu, eused = ENTRY_BLOCK;      // no block reserved yet
+    unsigned n_entries = 0;
+    auto emit = [&](bool has, unsigned tile, unsigned mask) {
+        const unsigned nz = __ballot_sync(FULL, has);
+        const unsigned c = __popc(nz);
+        if (c == 0) return;
+        if (eused + c > (unsigned)ENTRY_BLOCK) {
+            // pad the rest of the current block with empty entries, reserve the next one
+            if (ebase != 0xffffffffu)
+                for (unsigned e = eused + lane; e < (unsigned)ENTRY_BLOCK; e += 32) {
+                    SL.ent_tile[ebase + e] = bucket0; SL.ent_warp[ebase + e] = 0u; SL.ent_mask[ebase + e] = 0u;
+                }
+            unsigned nb = 0;
+            if (lane == 0) nb = (unsigned)atomicAdd(SL.counter, (unsigned long long)ENTRY_BLOCK);
+            nb = __shfl_sync(FULL, nb, 0);
+            if ((unsigned long long)nb + ENTRY_BLOCK > (unsigned long long)SL.cap) {     // cannot happen with the worst-case capacity
+                if (lane == 0) atomicExch(SL.overflow, 1u);
+                ebase = 0xffffffffu; eused = ENTRY_BLOCK;
+                return;
+            }
+            ebase = nb; eused = 0;
+        }
+        if (has) {
+            const unsigned pos = ebase + eused + __popc(nz & ((1u << lane) - 1u));
+            SL.ent_tile[pos] = bucket0 + tile; SL.ent_warp[pos] = my_warp; SL.ent_mask[pos] = mask;
+        }
+        eused += c;
+        n_entries += c;
+    };
+
+    const float* __restrict__ cbx = kde->cboxes;
+    const float* __restrict__ sbx = kde->sboxes;
+    const float* __restrict__ bx = kde->boxes;
+    const int s_end = (ntiles + SG - 1) / SG;
+#pragma unroll 1
+    for (int s_base = 0; s_base < s_end; s_base += CG) {
+        const bool need_c = alive && !(box_lb<D>(cbx + (size_t)(s_base / CG) * 2 * D, q2[0]) + negm > CULL_MARGIN);
+        if (!__any_sync(FULL, need_c)) continue;
+        // super-box tests, one query per lane: lane j keeps the ballot of super-box s_base + j
+        unsigned smask = 0u;
+        const int nsb = s_end - s_base < CG ? s_end - s_base : CG;
+#pragma unroll 2
+        for (int j = 0; j < nsb; j++) {
+            const float* b = sbx + (size_t)(s_base + j) * 2 * D;
+            float lb = 0.f;
+            bool valid = true;
+#pragma unroll
+            for (int k = 0; k < D; k++) {
+                const float lo = __ldg(b + k), hi = __ldg(b + D + k);
+                if (k == 0) valid = (lo <= hi);
+                const float gap = fmaxf(fmaxf(lo - q2[0][k], q2[0][k] - hi), 0.f);
+                lb = fmaf(gap, gap, lb);
+            }
+            const bool need = alive && valid && !(lb + negm > CULL_MARGIN);
+            const unsigned bal = __ballot_sync(FULL, need);
+            if (lane == j) smask = bal;
+        }
+        // tile tests, one tile per lane (two super-boxes per pass), against the queries of the super-box's ballot only
+        unsigned act = __ballot_sync(FULL, smask != 0u);
+        while (act) {
+            const int ja = __ffs(act) - 1;
+            act &= act - 1u;
+            int jb = -1;
+            if (act) { jb = __ffs(act) - 1; act &= act - 1u; }
+            const int j = (lane < 16) ? ja : jb;
+            unsigned qm = __shfl_sync(FULL, smask, j < 0 ? 0 : j);
+            const int t = (s_base + (j < 0 ? 0 : j)) * SG + (lane & 15);
+            if (j < 0 || t >= ntiles) qm = 0u;
+            float lo[D], hi[D];
+            {
+                const int tc = t < ntiles ? t : ntiles - 1;
+                const float* b = bx + (size_t)tc * 2 * D;
+                if (D % 4 == 0) {
+#pragma unroll
+                    for (int k = 0; k < D; k += 4) {
+                        const float4 a = __ldg(reinterpret_cast<const float4*>(b + k));
+                        const float4 c = __ldg(reinterpret_cast<const float4*>(b + D + k));
+                        lo[k] = a.x; lo[k + 1] = a.y; lo[k + 2] = a.z; lo[k + 3] = a.w;
+                        hi[k] = c.x; hi[k + 1] = c.y; hi[k + 2] = c.z; hi[k + 3] = c.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < D; k++) { lo[k] = __ldg(b + k); hi[k] = __ldg(b + D + k); }
+                }
+            }
+            if (!(lo[0] <= hi[0])) qm = 0u;                               // tile without weight
+            unsigned tmask = 0u;
+            while (__any_sync(FULL, qm != 0u)) {
+                const bool on = qm != 0u;
+                const int i = on ? 31 - __clz(qm) : 0;
+                qm &= ~(1u << i);                                         // 0 stays 0
+                const float* qrow = rows + i * QS;
+                float lb = 0.f;
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    const float zq = qrow[k];
+                    const float gap = fmaxf(fmaxf(lo[k] - zq, zq - hi[k]), 0.f);
+                    lb = fmaf(gap, gap, lb);
+                }
+                if (on && !(lb + qrow[D] > CULL_MARGIN)) tmask |= 1u << i;
+            }
+            emit(tmask != 0u, (unsigned)t, tmask);
+        }
+    }
+    // pad the tail of the last block
+    if (ebase != 0xffffffffu)
+        for (unsigned e = eused + lane; e < (unsigned)ENTRY_BLOCK; e += 32) {
+            SL.ent_tile[ebase + e] = bucket0; SL.ent_warp[ebase + e] = 0u; SL.ent_mask[ebase + e] = 0u;
+        }
+    if (job.stats && lane == 0) {
+        atomicAdd(&job.stats[2], (unsigned long long)((unsigned)ntiles - n_entries));   // tiles no query of the warp needs
+        atomicAdd(&job.stats[3], (unsigned long long)ntiles);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bucket: counting sort of the entries by tile, buckets [b_lo, b_hi) per pass
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void entry_slice(const SparseLaunch& SL, unsigned& a, unsigned& b)
+{
+    unsigned long long n = *SL.counter;
+    if (n > SL.cap) n = SL.cap;
+    const unsigned per = (unsigned)((n + NB_CTAS - 1) / NB_CTAS);
+    a = blockIdx.x * per;
+    b = a + per;
+    if (a > n) a = (unsigned)n;
+    if (b > n) b = (unsigned)n;
+}
+
+__global__ void __launch_bounds__(256) skb_hist_kernel(const SparseLaunch* __restrict__ SLp, unsigned b_lo, unsigned b_hi)
+{
+    extern __shared__ unsigned sh[];
+    const SparseLaunch& SL = *SLp;
+    const unsigned nb = b_hi - b_lo;
+    for (unsigned i = threadIdx.x; i < nb; i += blockDim.x) sh[i] = 0u;
+    __syncthreads();
+    unsigned a, b;
+    entry_slice(SL, a, b);
+    for (unsigned i = a + threadIdx.x; i < b; i += blockDim.x) {
+        const unsigned t = SL.ent_tile[i];
+        if (t >= b_lo && t < b_hi && SL.ent_mask[i] != 0u) atomicAdd(&sh[t - b_lo], 1u);
+    }
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < nb; i += blockDim.x) SL.hist[(size_t)i * NB_CTAS + blockIdx.x] = sh[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) SL.hist[(size_t)nb * NB_CTAS] = 0u;      // the scan leaves the total here
+}
+
+__global__ void __launch_bounds__(256) skb_scatter_kernel(const SparseLaunch* __restrict__ SLp, unsigned b_lo, unsigned b_hi)
+{
+    extern __shared__ unsigned sh[];
+    const SparseLaunch& SL = *SLp;
+    const unsigned nb = b_hi - b_lo;
+    for (unsigned i = threadIdx.x; i < nb; i += blockDim.x) sh[i] = SL.hist[(size_t)i * NB_CTAS + blockIdx.x];
+    __syncthreads();
+    unsigned a, b;
+    entry_slice(SL, a, b);
+    for (unsigned i = a + threadIdx.x; i < b; i += blockDim.x) {
+        const unsigned t = SL.ent_tile[i];
+        const unsigned m = SL.ent_mask[i];
+        if (t >= b_lo && t < b_hi && m != 0u) {
+            const unsigned pos = atomicAdd(&sh[t - b_lo], 1u);
+            SL.srt_tile[pos] = t; SL.srt_warp[pos] = SL.ent_warp[i]; SL.srt_mask[pos] = m;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// evaluate
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(32 * EVAL_WARPS, 2)
+skb_eval_kernel(const SparseLaunch* __restrict__ SLp, unsigned nbuckets_pass)
+{
+    constexpr int TN = tile_points(D);
+    constexpr int QS = sp_qstride(D);
+    constexpr int TILE_FLOATS = sp_tile_floats(D);
+    constexpr int STAGE_FLOATS = stage_floats(D);
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float* slot = reinterpret_cast<float*>(smem_raw) + (size_t)wid * TILE_FLOATS;                 // this warp's tile
+    unsigned* tab = reinterpret_cast<unsigned*>(reinterpret_cast<float*>(smem_raw) + (size_t)EVAL_WARPS * TILE_FLOATS) + wid * 4 * EVAL_EB;
+    unsigned* s_scan = tab;                      // inclusive pair counts
+    unsigned* s_tile = tab + EVAL_EB;
+    unsigned* s_warp = tab + 2 * EVAL_EB;
+    unsigned* s_mask = tab + 3 * EVAL_EB;
+
+    const SparseLaunch& SL = *SLp;
+    const unsigned n = SL.hist[(size_t)nbuckets_pass * NB_CTAS];          // sorted entries of this pass (total of the scan)
+    const unsigned nblk = (n + EVAL_EB - 1) / EVAL_EB;
+    const unsigned gw = blockIdx.x * EVAL_WARPS + wid, nw = gridDim.x * EVAL_WARPS;
+    unsigned long long n_pairs = 0;
+
+#pragma unroll 1
+    for (unsigned blk = gw; blk < nblk; blk += nw) {
+        __syncwarp();
+        // ---- the block's 64 entries (two per lane) and the inclusive scan of their pair counts ----
+        unsigned pc[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const unsigned e = blk * EVAL_EB + h * 32 + lane;
+            const bool in = e < n;
+            const unsigned m = in ? SL.srt_mask[e] : 0u;
+            s_tile[h * 32 + lane] = in ? SL.srt_tile[e] : 0xffffffffu;
+            s_warp[h * 32 + lane] = in ? SL.srt_warp[e] : 0u;
+            s_mask[h * 32 + lane] = m;
+            pc[h] = __popc(m);
+        }
+        unsigned carry = 0u;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            unsigned incl = pc[h];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            incl += carry;
+            s_scan[h * 32 + lane] = incl;
+            carry = __shfl_sync(FULL, incl, 31);
+        }
+        const unsigned total = carry;
+        __syncwarp();
+
+        // ---- tile by tile (sorted: the entries of a tile are contiguous, and so are their ranks) ----
+        unsigned r0 = 0u;
+        int e_first = 0;                              // first entry of the current tile
+#pragma unroll 1
+        while (r0 < total) {
+            // skip entries that end at or before r0 (none in practice: padding entries never reach the sorted list)
+            while (e_first < EVAL_EB && s_scan[e_first] <= r0) e_first++;
+            const unsigned cur = s_tile[e_first];
+            // last entry of this tile: entries are sorted, so compare each lane's entries with `cur`
+            const unsigned m0 = __ballot_sync(FULL, s_tile[lane] == cur);
+            const unsigned m1 = __ballot_sync(FULL, s_tile[32 + lane] == cur);
+            const int e_last = m1 ? 32 + (31 - __clz(m1)) : (31 - __clz(m0));
+            const unsigned r_end = s_scan[e_last];
+
+            // which job, which tile
+            int jsel = 0;
+#pragma unroll 1
+            for (int j = 1; j < SL.njobs; j++)
+                if (SL.sj[SL.jobs_of_group[j]].tile_base <= (int)cur) jsel = j;
+            const SparseJob& sj = SL.sj[SL.jobs_of_group[jsel]];
+            const float* __restrict__ gt = sj.tiles + (size_t)(cur - (unsigned)sj.tile_base) * STAGE_FLOATS;
+            // stage the tile (coordinates + weights) in this warp's slot
+            __syncwarp();
+#pragma unroll
+            for (int i = lane; i < TILE_FLOATS / 4; i += 32)
+                reinterpret_cast<float4*>(slot)[i] = __ldg(reinterpret_cast<const float4*>(gt) + i);
+            __syncwarp();
+
+#pragma unroll 1
+            for (unsigned r = r0; r < r_end; r += 64u) {
+                // this lane's two queries: ranks ra, ra + 1 among the tile's needers (the second may fall off the end)
+                const unsigned ra = r + 2u * (unsigned)lane;
+                if (ra < r_end) {
+                    unsigned qv[2];
+                    const bool two = ra + 1u < r_end;
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const unsigned rk = (h == 1 && !two) ? ra : ra + (unsigned)h;
+                        // entry e in [e_first, e_last] with scan[e - 1] <= rk < scan[e]
+                        int lo = e_first, hi = e_last;
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if (s_scan[mid] > rk) hi = mid; else lo = mid + 1;
+                        }
+                        const unsigned before = lo ? s_scan[lo - 1] : 0u;
+                        qv[h] = s_warp[lo] * 32u + (unsigned)nth_set_bit(s_mask[lo], rk - before);
+                    }
+                    float qq[2][D], nm[2];
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const float4* qrow = reinterpret_cast<const float4*>(sj.qz + (size_t)qv[h] * QS);
+                        float rr[QS];
+#pragma unroll
+                        for (int k = 0; k < QS / 4; k++) {
+                            const float4 v = __ldg(qrow + k);
+                            rr[4 * k] = v.x; rr[4 * k + 1] = v.y; rr[4 * k + 2] = v.z; rr[4 * k + 3] = v.w;
+                        }
+#pragma unroll
+                        for (int k = 0; k < D; k++) qq[h][k] = rr[k];
+                        nm[h] = rr[D];
+                    }
+                    u64 sum2[2];
+                    float unused[2];
+                    sum2[0] = pk(0.f, 0.f);
+                    sum2[1] = pk(0.f, 0.f);
+#pragma unroll 1
+                    for (int pt = 0; pt < TN; pt += 4) {
+                        StepOperands<D> A;
+                        A.template load<true>(slot, pt);
+                        step_compute<D, 2, false, false>(A, qq, nm, sum2, unused);
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        if (h == 1 && !two) break;
+                        float sl, sh_;
+                        upk(sum2[h], sl, sh_);
+                        const float s = sl + sh_;
+                        if (s > 0.f) {
+                            // s = (hi + f) 2^-64 with f in [0, 1): 128-bit fixed point, LSB 2^-128
+                            const float t = s * FX_SCALE;
+                            const float fh = floorf(t);
+                            const unsigned long long lo64 = __float2ull_rn((t - fh) * FX_SCALE);
+                            unsigned long long hi64 = (unsigned long long)fh;
+                            unsigned long long* acc = sj.acc + (size_t)qv[h] * 2;
+                            const unsigned long long old = atomicAdd(acc, lo64);
+                            if (old + lo64 < old) hi64 += 1ull;                   // carry
+                            if (hi64) atomicAdd(acc + 1, hi64);
+                        }
+                    }
+                    n_pairs += (unsigned)TN * (two ? 2u : 1u);
+                }
+            }
+            r0 = r_end;
+            e_first = e_last + 1;
+        }
+    }
+    if (SL.stats) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n_pairs += __shfl_xor_sync(FULL, n_pairs, o);
+        if (lane == 0 && n_pairs) atomicAdd(&SL.stats[1], n_pairs / 32ull);      // counters are "per lane at warp level": x 32 = pairs
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+skb_sparse_fin_kernel(const __grid_constant__ ScoreLaunch L, const SparseLaunch* __restrict__ SLp, int first, int count, long long M)
+{
+    const SparseLaunch& SL = *SLp;
+    const int f0 = first + (count == 1 ? (int)blockIdx.y : 0);            // ungrouped launches finalize one job per blockIdx.y
+    const long long Mj = count == 1 ? SL.sj[f0].M : M;
+    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= Mj) return;
+    const bool overflow = *SL.overflow != 0u;
+    finalize_query_with(L.fin, f0, count, v, [&](int f, long long vv, double& mstar, double& S) {
+        const SparseJob& sj = SL.sj[f];
+        const float negm = sj.qz[(size_t)vv * sj.qs + sj.D];
+        const unsigned long long lo = sj.acc[(size_t)vv * 2], hi = sj.acc[(size_t)vv * 2 + 1];
+        S = __dadd_rn(__dmul_rn((double)hi, 5.421010862427522e-20), __dmul_rn((double)lo, 2.938735877055719e-39));   // 2^-64, 2^-128
+        mstar = -(double)negm;
+        if (overflow || negm != negm) { S = NAN; mstar = 0.0; }
+    });
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <int D>
+static cudaError_t launch_group_d(const ScoreLaunch& L, int nl, const SparseLaunch& SLh, const SparseLaunch* SLd,
+                                  long long max_rows, int nbuckets, void* scan_tmp, size_t scan_tmp_bytes, int sms, cudaStream_t st)
+{
+    cudaError_t e;
+    const long long nwarps = (max_rows + 31) / 32;
+    dim3 pg((unsigned)((nwarps + PLAN_WARPS - 1) / PLAN_WARPS), (unsigned)nl, 1);
+    skb_plan_kernel<D><<<pg, 32 * PLAN_WARPS, 0, st>>>(L, SLd);
+    count_launch();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    const size_t eval_smem = (size_t)EVAL_WARPS * sp_tile_floats(D) * 4 + (size_t)EVAL_WARPS * 4 * EVAL_EB * 4;
+    if ((e = cudaFuncSetAttribute(skb_eval_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_smem)) != cudaSuccess) return e;
+    for (int b_lo = 0; b_lo < nbuckets; b_lo += MAX_BUCKETS) {
+        const int b_hi = b_lo + MAX_BUCKETS < nbuckets ? b_lo + MAX_BUCKETS : nbuckets;
+        const int nb = b_hi - b_lo;
+        const size_t hsmem = (size_t)nb * 4;
+        skb_hist_kernel<<<NB_CTAS, 256, hsmem, st>>>(SLd, (unsigned)b_lo, (unsigned)b_hi);
+        size_t tb = scan_tmp_bytes;
+        if ((e = cub::DeviceScan::ExclusiveSum(scan_tmp, tb, SLh.hist, SLh.hist, nb * NB_CTAS + 1, st)) != cudaSuccess) return e;
+        skb_scatter_kernel<<<NB_CTAS, 256, hsmem, st>>>(SLd, (unsigned)b_lo, (unsigned)b_hi);
+        skb_eval_kernel<D><<<2 * sms, 32 * EVAL_WARPS, eval_smem, st>>>(SLd, (unsigned)nb);
+        count_launch(5);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+size_t sparse_scan_temp_bytes()
+{
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (unsigned*)nullptr, (unsigned*)nullptr, MAX_BUCKETS * NB_CTAS + 1);
+    return bytes;
+}
+
+cudaError_t sparse_prepare()
+{
+    static bool done = false;
+    if (done) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(skb_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BUCKETS * 4);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(skb_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BUCKETS * 4);
+    if (e != cudaSuccess) return e;
+    done = true;
+    return cudaSuccess;
+}
+
+cudaError_t launch_sparse_group(int D, const ScoreLaunch& L, int nl, const SparseLaunch& SLh, const SparseLaunch* SLd,
+                                long long max_rows, int nbuckets, void* scan_tmp, size_t scan_tmp_bytes, int sms, cudaStream_t st)
+{
+    switch (D) {
+#define SKB_CASE(d) case d: return launch_group_d<d>(L, nl, SLh, SLd, max_rows, nbuckets, scan_tmp, scan_tmp_bytes, sms, st);
+        SKB_CASE(1) SKB_CASE(2) SKB_CASE(3) SKB_CASE(4) SKB_CASE(5) SKB_CASE(6) SKB_CASE(7) SKB_CASE(8)
+        SKB_CASE(9) SKB_CASE(10) SKB_CASE(11) SKB_CASE(12) SKB_CASE(13) SKB_CASE(14) SKB_CASE(15) SKB_CASE(16)
+#undef SKB_CASE
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_sparse_finalize(const ScoreLaunch& L, const SparseLaunch* SLd, int first, int count, int njobs_y,
+                                   long long max_rows, cudaStream_t st)
+{
+    dim3 grid((unsigned)((max_rows + 255) / 256), (unsigned)njobs_y, 1);
+    skb_sparse_fin_kernel<<<grid, 256, 0, st>>>(L, SLd, first, count, max_rows);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace skb
