@@ -294,9 +294,13 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
             void* p = nullptr;
             SKB_CUDA(ar.get(&p, (size_t)dj.M * qs * sizeof(float)));
             SLh.sj[j].qz = reinterpret_cast<float*>(p);
-            SKB_CUDA(ar.get(&p, (size_t)dj.M * 16));
-            SKB_CUDA(cudaMemsetAsync(p, 0, (size_t)dj.M * 16, st));
+            SKB_CUDA(ar.get(&p, (size_t)dj.M * 32));
+            SKB_CUDA(cudaMemsetAsync(p, 0, (size_t)dj.M * 32, st));
             SLh.sj[j].acc = reinterpret_cast<unsigned long long*>(p);
+            SKB_CUDA(ar.get(&p, (size_t)dj.M * 4));
+            SKB_CUDA(cudaMemsetAsync(p, 0x7f, (size_t)dj.M * 4, st));
+            SLh.sj[j].newbest = reinterpret_cast<float*>(p);
+            SLh.sj[j].ref_bias = dj.h->hk.ref_bias;
             SLh.sj[j].tiles = dj.h->tiles;
             SLh.sj[j].M = dj.M;
             SLh.sj[j].qs = qs;
@@ -307,6 +311,7 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
         SKB_CUDA(cudaMemsetAsync(p, 0, 64, st));
         SLh.counter = reinterpret_cast<unsigned long long*>(p);
         SLh.overflow = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(p) + 16);
+        SLh.nflag = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(p) + 8);
         SLh.stats = stats;
         // worst-case number of device descriptors: one per sub-chunk per dimension group (bounded below)
         sl_cap = 0;
@@ -407,7 +412,7 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
             SLh.vend = (w0 + sub_warps) * 32 < max_rows ? (w0 + sub_warps) * 32 : max_rows;
             SparseLaunch* SLd = SLd_all + n_sl++;
             SKB_CUDA(cudaMemcpyAsync(SLd, &SLh, sizeof(SparseLaunch), cudaMemcpyHostToDevice, st));   // pageable source: staged before return
-            SKB_CUDA(cudaMemsetAsync(SLh.counter, 0, 8, st));
+            SKB_CUDA(cudaMemsetAsync(SLh.counter, 0, 16, st));       // entry counter + flag counter
             SKB_CUDA(launch_sparse_group(D, L, nl, SLh, SLd, SLh.vend - SLh.vbeg, nbuckets, scan_tmp, scan_bytes,
                                          jobs[j0].h->sms, st));
         }

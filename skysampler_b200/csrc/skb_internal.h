@@ -168,8 +168,10 @@ struct ScoreLaunch {
 struct SparseJob {
     const float* tiles;          // the KDE's tile array
     float* qz;                   // [M][qs] prescaled whitened query rows: z[0..D), -m, padding
-    unsigned long long* acc;     // [M][2] 128-bit fixed-point sums (lo, hi), LSB 2^-128 relative to 2^m
+    unsigned long long* acc;     // [M][4] 256-bit fixed-point sums (limbs low to high), LSB 2^-128 relative to 2^m
+    float* newbest;              // [M] 0x7f7f7f7f, or the exact smallest weighted exponent of a query whose reference overflowed
     long long M;
+    float ref_bias;
     int tile_base;               // first bucket of this job within its dimension group
     int qs;
     int D;
@@ -187,6 +189,7 @@ struct SparseLaunch {
     unsigned* srt_mask;
     unsigned long long* counter;         // entries reserved so far
     unsigned* overflow;                  // set if the entry list ever overflowed (results are then NaN)
+    unsigned* nflag;                     // queries flagged for re-referencing in this sub-chunk
     unsigned* hist;                      // [buckets of a pass][NB_CTAS] (+1): histogram, scanned in place
     unsigned long long* stats;           // diagnostic counters or NULL
     unsigned long long cap;

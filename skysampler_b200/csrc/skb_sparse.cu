@@ -23,24 +23,62 @@
 //             sharding gives the same bits) although the evaluation order is not
 //   finalize  accumulators -> fp64 (m, S) -> log p, ratio and accept test
 //
-// The exponent reference is fixed per query before the first tile: after the plan step every point satisfies
-// |c dz|^2 - log2 w >= best - FAR_LIMIT, so no term exceeds 2^(FAR_LIMIT - bias) and the fixed-point range is never left.
+// The exponent reference m is fixed per query by the plan step (an upper bound of the smallest weighted exponent, from
+// the home super-box).  The accumulator spans 2^-128 .. 2^128 relative to 2^m, i.e. points up to ~190 binades closer than
+// the reference are simply absorbed.  A (query, tile) sum beyond that (the home estimate missed the true nearest point
+// by more than 190 binades: far-tail queries) flags the query with the tile's exact minimum (atomicMin, order
+// independent); flagged queries are re-referenced to that minimum — it IS the global one, every unflagged tile being
+// farther — and their entries are evaluated again: a superset of what the new reference needs.
 #include "skb_score_common.cuh"
 #include <cub/device/device_scan.cuh>
 
 namespace skb {
 
-constexpr float FAR_LIMIT = 64.f;                 // references farther than this from every home point are refined exactly
+constexpr float SUM_LIMIT = 1.6225928e32f;         // 2^107: a (query, tile) sum at or above this re-references the query
+constexpr float NEWBEST_NONE = 3.0e38f;           // newbest[] holds 0x7f7f7f7f (3.39e38) until a query is flagged
 constexpr int PLAN_WARPS = 4;                     // warps per CTA of the plan kernel (independent of each other)
 constexpr int ENTRY_BLOCK = 256;                  // entries a plan warp reserves at a time (one global atomic per block)
 constexpr int EVAL_EB = 64;                       // sorted entries per evaluate work unit (two per lane)
-constexpr int EVAL_WARPS = 8;
+#ifndef SKB_EVAL_WARPS
+#define SKB_EVAL_WARPS 8
+#endif
+#ifndef SKB_EVAL_MINB
+#define SKB_EVAL_MINB 2
+#endif
+constexpr int EVAL_WARPS = SKB_EVAL_WARPS;
 constexpr int NB_CTAS = 128;                      // CTAs of the bucket kernels (slices of the entry list)
 constexpr int MAX_BUCKETS = 48 * 1024;            // tiles per bucket pass (shared-memory histogram)
-constexpr float FX_SCALE = 18446744073709551616.f;   // 2^64
+constexpr int ACC_LIMBS = 4;                      // 256-bit fixed-point accumulator per query, LSB 2^-128 (relative to 2^m)
 
 __host__ __device__ constexpr int sp_qstride(int D) { return (D + 4) & ~3; }                  // z[0..D), -m, padding to 16 B
 __host__ __device__ constexpr int sp_tile_floats(int D) { return (D + 1) * tile_points(D); }  // coordinates + weights
+
+// acc += s, exactly: s = mant 2^(e-150) lands at bit e - 22 of the accumulator (unit 2^-128); integer atomics with carry
+// propagation are associative, so the sum does not depend on the order in which (query, tile) sums arrive.  Callers pass
+// sums below SUM_LIMIT = 2^107 only, so the top limb cannot overflow.
+__device__ __forceinline__ void fx_add(unsigned long long* __restrict__ acc, float s)
+{
+    if (!(s > 0.f)) return;
+    const unsigned bits = __float_as_uint(s);
+    const int e = (int)((bits >> 23) & 0xffu);
+    unsigned long long mant = (unsigned long long)(bits & 0x7fffffu) | (e ? 0x800000ull : 0ull);
+    int p = (e ? e : 1) - 22;
+    if (p < 0) {                                   // below 2^-128: the low bits fall off (at least 38 bits under the reference term)
+        mant = (-p >= 24) ? 0ull : (mant >> (-p));
+        p = 0;
+    }
+    if (mant == 0ull) return;
+    int limb = p >> 6;
+    const int sh = p & 63;
+    const unsigned long long lo = mant << sh;
+    unsigned long long hi = sh > 40 ? (mant >> (64 - sh)) : 0ull;
+    const unsigned long long old = atomicAdd(acc + limb, lo);
+    if (old + lo < old) hi += 1ull;
+    for (limb++; hi != 0ull && limb < ACC_LIMBS; limb++) {
+        const unsigned long long o2 = atomicAdd(acc + limb, hi);
+        hi = (o2 + hi < o2) ? 1ull : 0ull;
+    }
+}
 
 // position of the n-th (0-based) set bit of w; n < popc(w)
 __device__ __forceinline__ int nth_set_bit(unsigned w, unsigned n)
@@ -92,40 +130,74 @@ __device__ __forceinline__ float coop_scan_tile(const float* __restrict__ tile, 
     return b;
 }
 
-// Exact branch and bound for ONE query (broadcast to the warp) whose home estimate `best` is far from everything: every
-// tile whose box comes closer than best - slack is scanned.  Lanes = boxes at each level.  Afterwards every point has
-// |c dz|^2 >= best - slack.
+// (value, index) argmin over the warp; ties keep the smaller index; result is warp uniform
+__device__ __forceinline__ void warp_argmin(float& v, int& i)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+}
+
+// Exponent reference of ONE query (coordinates broadcast to the warp), warp cooperative with lanes = boxes / points:
+//   (1) the super-box nearest to the query by box distance (exact branch and bound over chunk boxes -> super-boxes): "home";
+//   (2) its tiles are scanned in order of box distance for the smallest weighted exponent |c dz|^2 - log2 w, as long as a
+//       tile's box can still beat the best point found.
+// A real point's exponent is an upper bound of the true minimum, which is all the window needs for accuracy; a tight
+// one (the nearest neighbour usually lives in the home super-box) is what lets the box tests cull.  Should a point far
+// below it turn up later, the evaluate step detects the overflow and the query is re-referenced exactly (see there).
 template <int D>
-__device__ __forceinline__ float coop_refine_reference(const KdeDev* __restrict__ kde, int ntiles, const float (&zq)[D],
-                                                       float best, float slack, int lane)
+__device__ __forceinline__ float coop_home_reference(const KdeDev* __restrict__ kde, int ntiles, const float (&zq)[D], int lane)
 {
     constexpr unsigned FULL = 0xffffffffu;
     const bool has_w = kde->has_w != 0;
     const int nchunk = kde->nchunk, nsuper = kde->nsuper;
+    // nearest chunk box
+    float cb = INFINITY;
+    int ci = 0;
 #pragma unroll 1
     for (int c0 = 0; c0 < nchunk; c0 += 32) {
         const int c = c0 + lane;
-        const float lbc = c < nchunk ? box_lb<D>(kde->cboxes + (size_t)c * 2 * D, zq) : INFINITY;
-        unsigned cm = __ballot_sync(FULL, lbc < best - slack);
-        while (cm) {
-            const int cc = c0 + __ffs(cm) - 1;
-            cm &= cm - 1u;
-            const int s = cc * CG + (lane & 15);
-            const float lbs = (lane < CG && s < nsuper) ? box_lb<D>(kde->sboxes + (size_t)s * 2 * D, zq) : INFINITY;
-            unsigned sm = __ballot_sync(FULL, lbs < best - slack);
-            while (sm) {
-                const int ss = cc * CG + __ffs(sm) - 1;
-                sm &= sm - 1u;
-                const int t = ss * SG + (lane & 15);
-                const float lbt = (lane < SG && t < ntiles) ? box_lb<D>(kde->boxes + (size_t)t * 2 * D, zq) : INFINITY;
-                unsigned tm = __ballot_sync(FULL, lbt < best - slack);
-                while (tm) {
-                    const int tt = ss * SG + __ffs(tm) - 1;
-                    tm &= tm - 1u;
-                    best = fminf(best, coop_scan_tile<D>(kde->tiles + (size_t)tt * stage_floats(D), zq, has_w, lane));
-                }
-            }
+        const float lb = c < nchunk ? box_lb<D>(kde->cboxes + (size_t)c * 2 * D, zq) : INFINITY;
+        if (lb < cb) { cb = lb; ci = c; }
+    }
+    warp_argmin(cb, ci);
+    // nearest super-box: the nearest chunk's first, then every chunk whose box is closer than the best super-box so far
+    float sb = INFINITY;
+    int si = ci * CG;
+    auto scan_chunk = [&](int c) {
+        const int s = c * CG + (lane & 15);
+        float lb = (lane < CG && s < nsuper) ? box_lb<D>(kde->sboxes + (size_t)s * 2 * D, zq) : INFINITY;
+        int idx = s;
+        warp_argmin(lb, idx);
+        if (lb < sb) { sb = lb; si = idx; }
+    };
+    scan_chunk(ci);
+#pragma unroll 1
+    for (int c0 = 0; c0 < nchunk; c0 += 32) {
+        const int c = c0 + lane;
+        const float lb = (c < nchunk && c != ci) ? box_lb<D>(kde->cboxes + (size_t)c * 2 * D, zq) : INFINITY;
+        unsigned m = __ballot_sync(FULL, lb < sb);
+        while (m) {
+            const int cc = c0 + __ffs(m) - 1;
+            m &= m - 1u;
+            scan_chunk(cc);
         }
+    }
+    // tiles of the home super-box, nearest box first
+    const int t = si * SG + (lane & 15);
+    const float lbt = (lane < SG && t < ntiles) ? box_lb<D>(kde->boxes + (size_t)t * 2 * D, zq) : INFINITY;
+    float best = INFINITY;
+    unsigned todo = __ballot_sync(FULL, lbt < INFINITY);
+    while (todo) {
+        float v = ((todo >> lane) & 1u) ? lbt : INFINITY;
+        int l = lane;
+        warp_argmin(v, l);
+        if (!(v < best)) break;
+        todo &= ~(1u << l);
+        best = fminf(best, coop_scan_tile<D>(kde->tiles + (size_t)(si * SG + (l & 15)) * stage_floats(D), zq, has_w, lane));
     }
     return best;
 }
@@ -162,23 +234,23 @@ skb_plan_kernel(const __grid_constant__ ScoreLaunch L, const SparseLaunch* __res
     bool isnan_row = false;
 #pragma unroll
     for (int k = 0; k < D; k++) isnan_row |= (q2[0][k] != q2[0][k]);
-    float mref[1], bmin[1], nm2[1];
-    home_reference<D, 1>(kde, ntiles, q2, bmin, mref, nm2, alive && !isnan_row);
+    float mref = 0.f;
     {
-        unsigned farm = __ballot_sync(FULL, alive && !isnan_row && bmin[0] > FAR_LIMIT);
-        while (farm) {
-            const int src = __ffs(farm) - 1;
-            farm &= farm - 1u;
+        // one query at a time, the whole warp on it (lanes = boxes, then lanes = points)
+        unsigned todo = __ballot_sync(FULL, alive && !isnan_row);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1u;
             float zq[D];
 #pragma unroll
             for (int k = 0; k < D; k++) zq[k] = __shfl_sync(FULL, q2[0][k], src);
-            float best = __shfl_sync(FULL, bmin[0], src);
-            best = coop_refine_reference<D>(kde, ntiles, zq, best, FAR_LIMIT, lane);
-            if (lane == src && best < bmin[0]) { bmin[0] = best; mref[0] = floorf(best) - ref_bias; }
+            float best = coop_home_reference<D>(kde, ntiles, zq, lane);
+            if (!(best < 1.0e30f)) best = ref_bias;                  // inf rows (or padding only): finite reference
+            if (lane == src) mref = floorf(best) - ref_bias;
         }
     }
     // rows past the end of the table and NaN rows need nothing (a NaN row's -m is NaN: finalize propagates it)
-    const float negm = !alive ? INFINITY : (isnan_row ? NAN : -mref[0]);
+    const float negm = !alive ? INFINITY : (isnan_row ? NAN : -mref);
     alive = alive && !isnan_row;
 #pragma unroll
     for (int k = 0; k < D; k++) rows[lane * QS + k] = q2[0][k];
@@ -325,10 +397,11 @@ __device__ __forceinline__ void entry_slice(const SparseLaunch& SL, unsigned& a,
     if (b > n) b = (unsigned)n;
 }
 
-__global__ void __launch_bounds__(256) skb_hist_kernel(const SparseLaunch* __restrict__ SLp, unsigned b_lo, unsigned b_hi)
+__global__ void __launch_bounds__(256) skb_hist_kernel(const SparseLaunch* __restrict__ SLp, unsigned b_lo, unsigned b_hi, int redo)
 {
     extern __shared__ unsigned sh[];
     const SparseLaunch& SL = *SLp;
+    if (redo && *SL.nflag == 0u) return;
     const unsigned nb = b_hi - b_lo;
     for (unsigned i = threadIdx.x; i < nb; i += blockDim.x) sh[i] = 0u;
     __syncthreads();
@@ -343,10 +416,11 @@ __global__ void __launch_bounds__(256) skb_hist_kernel(const SparseLaunch* __res
     if (blockIdx.x == 0 && threadIdx.x == 0) SL.hist[(size_t)nb * NB_CTAS] = 0u;      // the scan leaves the total here
 }
 
-__global__ void __launch_bounds__(256) skb_scatter_kernel(const SparseLaunch* __restrict__ SLp, unsigned b_lo, unsigned b_hi)
+__global__ void __launch_bounds__(256) skb_scatter_kernel(const SparseLaunch* __restrict__ SLp, unsigned b_lo, unsigned b_hi, int redo)
 {
     extern __shared__ unsigned sh[];
     const SparseLaunch& SL = *SLp;
+    if (redo && *SL.nflag == 0u) return;
     const unsigned nb = b_hi - b_lo;
     for (unsigned i = threadIdx.x; i < nb; i += blockDim.x) sh[i] = SL.hist[(size_t)i * NB_CTAS + blockIdx.x];
     __syncthreads();
@@ -366,8 +440,8 @@ __global__ void __launch_bounds__(256) skb_scatter_kernel(const SparseLaunch* __
 // evaluate
 // ---------------------------------------------------------------------------------------------
 template <int D>
-__global__ void __launch_bounds__(32 * EVAL_WARPS, 2)
-skb_eval_kernel(const SparseLaunch* __restrict__ SLp, unsigned nbuckets_pass)
+__global__ void __launch_bounds__(32 * EVAL_WARPS, SKB_EVAL_MINB)
+skb_eval_kernel(const SparseLaunch* __restrict__ SLp, unsigned nbuckets_pass, int redo)
 {
     constexpr int TN = tile_points(D);
     constexpr int QS = sp_qstride(D);
@@ -384,6 +458,7 @@ skb_eval_kernel(const SparseLaunch* __restrict__ SLp, unsigned nbuckets_pass)
     unsigned* s_mask = tab + 3 * EVAL_EB;
 
     const SparseLaunch& SL = *SLp;
+    if (redo && *SL.nflag == 0u) return;                                  // nothing was flagged: the usual case
     const unsigned n = SL.hist[(size_t)nbuckets_pass * NB_CTAS];          // sorted entries of this pass (total of the scan)
     const unsigned nblk = (n + EVAL_EB - 1) / EVAL_EB;
     const unsigned gw = blockIdx.x * EVAL_WARPS + wid, nw = gridDim.x * EVAL_WARPS;
@@ -467,6 +542,14 @@ skb_eval_kernel(const SparseLaunch* __restrict__ SLp, unsigned nbuckets_pass)
                         const unsigned before = lo ? s_scan[lo - 1] : 0u;
                         qv[h] = s_warp[lo] * 32u + (unsigned)nth_set_bit(s_mask[lo], rk - before);
                     }
+                    bool want[2];
+                    want[0] = true;
+                    want[1] = two;
+                    if (redo) {                                           // second round: flagged queries only
+                        want[0] = sj.newbest[qv[0]] < NEWBEST_NONE;
+                        want[1] = two && sj.newbest[qv[1]] < NEWBEST_NONE;
+                        if (!want[0] && !want[1]) continue;
+                    }
                     float qq[2][D], nm[2];
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
@@ -474,7 +557,7 @@ skb_eval_kernel(const SparseLaunch* __restrict__ SLp, unsigned nbuckets_pass)
                         float rr[QS];
 #pragma unroll
                         for (int k = 0; k < QS / 4; k++) {
-                            const float4 v = __ldg(qrow + k);
+                            const float4 v = qrow[k];                       // (not __ldg: the fix-up kernel rewrites -m between rounds)
                             rr[4 * k] = v.x; rr[4 * k + 1] = v.y; rr[4 * k + 2] = v.z; rr[4 * k + 3] = v.w;
                         }
 #pragma unroll
@@ -493,23 +576,37 @@ skb_eval_kernel(const SparseLaunch* __restrict__ SLp, unsigned nbuckets_pass)
                     }
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
-                        if (h == 1 && !two) break;
+                        if (!want[h]) continue;
                         float sl, sh_;
                         upk(sum2[h], sl, sh_);
-                        const float s = sl + sh_;
-                        if (s > 0.f) {
-                            // s = (hi + f) 2^-64 with f in [0, 1): 128-bit fixed point, LSB 2^-128
-                            const float t = s * FX_SCALE;
-                            const float fh = floorf(t);
-                            const unsigned long long lo64 = __float2ull_rn((t - fh) * FX_SCALE);
-                            unsigned long long hi64 = (unsigned long long)fh;
-                            unsigned long long* acc = sj.acc + (size_t)qv[h] * 2;
-                            const unsigned long long old = atomicAdd(acc, lo64);
-                            if (old + lo64 < old) hi64 += 1ull;                   // carry
-                            if (hi64) atomicAdd(acc + 1, hi64);
+                        const float sm = sl + sh_;
+                        if (sm < SUM_LIMIT) {
+                            fx_add(sj.acc + (size_t)qv[h] * ACC_LIMBS, sm);
+                        } else if (!redo) {
+                            // a point far closer than the reference allows (or inf / NaN arithmetic): the tile's exact minimum
+                            // of the weighted exponent goes to newbest[] (absolute, >= 0: ordered like its bit pattern)
+                            float amin = INFINITY;
+#pragma unroll 1
+                            for (int pt = 0; pt < TN; pt++) {
+                                float a = fminf(-__log2f(slot[D * TN + pt]), LW_CAP);
+#pragma unroll
+                                for (int k = 0; k < D; k++) {
+                                    const float dz = qq[h][k] - slot[k * TN + pt];
+                                    a = fmaf(dz, dz, a);
+                                }
+                                amin = fminf(amin, a);
+                            }
+                            if (amin < NEWBEST_NONE) {
+                                atomicMin(reinterpret_cast<int*>(sj.newbest + qv[h]), __float_as_int(fmaxf(amin, 0.f)));
+                                atomicAdd(SL.nflag, 1u);
+                            } else {
+                                atomicExch(SL.overflow, 1u);               // NaN arithmetic on a finite row: fail loudly
+                            }
+                        } else {
+                            atomicExch(SL.overflow, 1u);                   // cannot happen after re-referencing
                         }
                     }
-                    n_pairs += (unsigned)TN * (two ? 2u : 1u);
+                    n_pairs += (unsigned)TN * ((want[0] ? 1u : 0u) + (want[1] ? 1u : 0u));
                 }
             }
             r0 = r_end;
@@ -521,6 +618,24 @@ skb_eval_kernel(const SparseLaunch* __restrict__ SLp, unsigned nbuckets_pass)
         for (int o = 16; o > 0; o >>= 1) n_pairs += __shfl_xor_sync(FULL, n_pairs, o);
         if (lane == 0 && n_pairs) atomicAdd(&SL.stats[1], n_pairs / 32ull);      // counters are "per lane at warp level": x 32 = pairs
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fix-up between the two evaluate rounds: flagged queries get the exact reference and a clean accumulator
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) skb_refix_kernel(const SparseLaunch* __restrict__ SLp)
+{
+    const SparseLaunch& SL = *SLp;
+    if (*SL.nflag == 0u) return;
+    const SparseJob& sj = SL.sj[SL.jobs_of_group[blockIdx.y]];
+    const long long vend = SL.vend < sj.M ? SL.vend : sj.M;
+    const long long v = SL.vbeg + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= vend) return;
+    const float nb = sj.newbest[v];
+    if (!(nb < NEWBEST_NONE)) return;
+    sj.qz[(size_t)v * sj.qs + sj.D] = -(floorf(nb) - sj.ref_bias);
+#pragma unroll
+    for (int k = 0; k < ACC_LIMBS; k++) sj.acc[(size_t)v * ACC_LIMBS + k] = 0ull;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -538,8 +653,10 @@ skb_sparse_fin_kernel(const __grid_constant__ ScoreLaunch L, const SparseLaunch*
     finalize_query_with(L.fin, f0, count, v, [&](int f, long long vv, double& mstar, double& S) {
         const SparseJob& sj = SL.sj[f];
         const float negm = sj.qz[(size_t)vv * sj.qs + sj.D];
-        const unsigned long long lo = sj.acc[(size_t)vv * 2], hi = sj.acc[(size_t)vv * 2 + 1];
-        S = __dadd_rn(__dmul_rn((double)hi, 5.421010862427522e-20), __dmul_rn((double)lo, 2.938735877055719e-39));   // 2^-64, 2^-128
+        const unsigned long long* a = sj.acc + (size_t)vv * ACC_LIMBS;
+        // limbs are worth 2^-128, 2^-64, 1, 2^64: summed top down in fp64
+        S = __dadd_rn(__dadd_rn(__dmul_rn((double)a[3], 18446744073709551616.0), (double)a[2]),
+                      __dadd_rn(__dmul_rn((double)a[1], 5.421010862427522e-20), __dmul_rn((double)a[0], 2.938735877055719e-39)));
         mstar = -(double)negm;
         if (overflow || negm != negm) { S = NAN; mstar = 0.0; }
     });
@@ -560,17 +677,31 @@ static cudaError_t launch_group_d(const ScoreLaunch& L, int nl, const SparseLaun
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     const size_t eval_smem = (size_t)EVAL_WARPS * sp_tile_floats(D) * 4 + (size_t)EVAL_WARPS * 4 * EVAL_EB * 4;
     if ((e = cudaFuncSetAttribute(skb_eval_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_smem)) != cudaSuccess) return e;
-    for (int b_lo = 0; b_lo < nbuckets; b_lo += MAX_BUCKETS) {
-        const int b_hi = b_lo + MAX_BUCKETS < nbuckets ? b_lo + MAX_BUCKETS : nbuckets;
-        const int nb = b_hi - b_lo;
-        const size_t hsmem = (size_t)nb * 4;
-        skb_hist_kernel<<<NB_CTAS, 256, hsmem, st>>>(SLd, (unsigned)b_lo, (unsigned)b_hi);
-        size_t tb = scan_tmp_bytes;
-        if ((e = cub::DeviceScan::ExclusiveSum(scan_tmp, tb, SLh.hist, SLh.hist, nb * NB_CTAS + 1, st)) != cudaSuccess) return e;
-        skb_scatter_kernel<<<NB_CTAS, 256, hsmem, st>>>(SLd, (unsigned)b_lo, (unsigned)b_hi);
-        skb_eval_kernel<D><<<2 * sms, 32 * EVAL_WARPS, eval_smem, st>>>(SLd, (unsigned)nb);
-        count_launch(5);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    const int npass = (nbuckets + MAX_BUCKETS - 1) / MAX_BUCKETS;
+    // round 0 evaluates everything; round 1 re-evaluates the queries flagged in round 0 (every kernel of round 1 returns at
+    // once when nothing was flagged; with a single bucket pass the sorted list of round 0 is still in place)
+    for (int redo = 0; redo < 2; redo++) {
+        if (redo) {
+            dim3 fg((unsigned)((max_rows + 255) / 256), (unsigned)nl, 1);
+            skb_refix_kernel<<<fg, 256, 0, st>>>(SLd);
+            count_launch();
+        }
+        for (int b_lo = 0; b_lo < nbuckets; b_lo += MAX_BUCKETS) {
+            const int b_hi = b_lo + MAX_BUCKETS < nbuckets ? b_lo + MAX_BUCKETS : nbuckets;
+            const int nb = b_hi - b_lo;
+            const size_t hsmem = (size_t)nb * 4;
+            if (!redo || npass > 1) {
+                skb_hist_kernel<<<NB_CTAS, 256, hsmem, st>>>(SLd, (unsigned)b_lo, (unsigned)b_hi, redo);
+                // (the scan of a skipped histogram is harmless: round 1's evaluate returns before reading it)
+                size_t tb = scan_tmp_bytes;
+                if ((e = cub::DeviceScan::ExclusiveSum(scan_tmp, tb, SLh.hist, SLh.hist, nb * NB_CTAS + 1, st)) != cudaSuccess) return e;
+                skb_scatter_kernel<<<NB_CTAS, 256, hsmem, st>>>(SLd, (unsigned)b_lo, (unsigned)b_hi, redo);
+                count_launch(4);
+            }
+            skb_eval_kernel<D><<<SKB_EVAL_MINB * sms, 32 * EVAL_WARPS, eval_smem, st>>>(SLd, (unsigned)nb, redo);
+            count_launch();
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        }
     }
     return cudaSuccess;
 }
