@@ -300,6 +300,9 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
             SKB_CUDA(ar.get(&p, (size_t)dj.M * 4));
             SKB_CUDA(cudaMemsetAsync(p, 0x7f, (size_t)dj.M * 4, st));
             SLh.sj[j].newbest = reinterpret_cast<float*>(p);
+            SKB_CUDA(ar.get(&p, (size_t)((dj.M + 31) / 32) * 4));
+            SKB_CUDA(cudaMemsetAsync(p, 0, (size_t)((dj.M + 31) / 32) * 4, st));
+            SLh.sj[j].wflag = reinterpret_cast<unsigned*>(p);
             SLh.sj[j].ref_bias = dj.h->hk.ref_bias;
             SLh.sj[j].tiles = dj.h->tiles;
             SLh.sj[j].M = dj.M;

@@ -170,6 +170,7 @@ struct SparseJob {
     float* qz;                   // [M][qs] prescaled whitened query rows: z[0..D), -m, padding
     unsigned long long* acc;     // [M][4] 256-bit fixed-point sums (limbs low to high), LSB 2^-128 relative to 2^m
     float* newbest;              // [M] 0x7f7f7f7f, or the exact smallest weighted exponent of a query whose reference overflowed
+    unsigned* wflag;             // [ceil(M / 32)] the same flags, one bit per query of a query warp
     long long M;
     float ref_bias;
     int tile_base;               // first bucket of this job within its dimension group

@@ -42,9 +42,13 @@ constexpr int EVAL_EB = 64;                       // sorted entries per evaluate
 #ifndef SKB_EVAL_WARPS
 #define SKB_EVAL_WARPS 8
 #endif
-#ifndef SKB_EVAL_MINB
-#define SKB_EVAL_MINB 2
+#ifndef SKB_EVAL_MINB_LO
+#define SKB_EVAL_MINB_LO 3      // resident CTAs per SM of the evaluate kernel for D <= 8 (<= 85 registers) ...
 #endif
+#ifndef SKB_EVAL_MINB_HI
+#define SKB_EVAL_MINB_HI 2      // ... and above
+#endif
+__host__ __device__ constexpr int eval_minb(int D) { return D <= 8 ? SKB_EVAL_MINB_LO : SKB_EVAL_MINB_HI; }
 constexpr int EVAL_WARPS = SKB_EVAL_WARPS;
 constexpr int NB_CTAS = 128;                      // CTAs of the bucket kernels (slices of the entry list)
 constexpr int MAX_BUCKETS = 48 * 1024;            // tiles per bucket pass (shared-memory histogram)
@@ -301,31 +305,70 @@ skb_plan_kernel(const __grid_constant__ ScoreLaunch L, const SparseLaunch* __res
     const float* __restrict__ cbx = kde->cboxes;
     const float* __restrict__ sbx = kde->sboxes;
     const float* __restrict__ bx = kde->boxes;
-    const int s_end = (ntiles + SG - 1) / SG;
-#pragma unroll 1
-    for (int s_base = 0; s_base < s_end; s_base += CG) {
-        const bool need_c = alive && !(box_lb<D>(cbx + (size_t)(s_base / CG) * 2 * D, q2[0]) + negm > CULL_MARGIN);
-        if (!__any_sync(FULL, need_c)) continue;
-        // super-box tests, one query per lane: lane j keeps the ballot of super-box s_base + j
-        unsigned smask = 0u;
-        const int nsb = s_end - s_base < CG ? s_end - s_base : CG;
-#pragma unroll 2
-        for (int j = 0; j < nsb; j++) {
-            const float* b = sbx + (size_t)(s_base + j) * 2 * D;
+    const int nchunk = kde->nchunk, nsuper = kde->nsuper;
+    // {lo, hi} of box b as packed pairs, or "empty" (no query can need it)
+    auto load_box = [&](const float* __restrict__ b, bool in_range, u64 (&box2)[D]) -> bool {
+        float lo[D], hi[D];
+        if (D % 4 == 0) {
+#pragma unroll
+            for (int k = 0; k < D; k += 4) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(b + k));
+                const float4 c = __ldg(reinterpret_cast<const float4*>(b + D + k));
+                lo[k] = a.x; lo[k + 1] = a.y; lo[k + 2] = a.z; lo[k + 3] = a.w;
+                hi[k] = c.x; hi[k + 1] = c.y; hi[k + 2] = c.z; hi[k + 3] = c.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < D; k++) { lo[k] = __ldg(b + k); hi[k] = __ldg(b + D + k); }
+        }
+#pragma unroll
+        for (int k = 0; k < D; k++) box2[k] = pk(lo[k], hi[k]);
+        return in_range && (lo[0] <= hi[0]);                              // (inf, -inf): a box without weight
+    };
+    // this lane's box against the queries of qm (walked highest bit first; the warp iterates until every lane is done)
+    auto test_box = [&](const u64 (&box2)[D], unsigned qm) -> unsigned {
+        unsigned out = 0u;
+        while (__any_sync(FULL, qm != 0u)) {
+            const bool on = qm != 0u;
+            const int i = on ? 31 - __clz(qm) : 0;
+            qm &= ~(1u << i);                                             // 0 stays 0
+            const float* qrow = rows + i * QS;
+            float r[QS];
+#pragma unroll
+            for (int k = 0; k < QS; k += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(qrow + k);
+                r[k] = v.x; r[k + 1] = v.y; r[k + 2] = v.z; r[k + 3] = v.w;
+            }
             float lb = 0.f;
-            bool valid = true;
 #pragma unroll
             for (int k = 0; k < D; k++) {
-                const float lo = __ldg(b + k), hi = __ldg(b + D + k);
-                if (k == 0) valid = (lo <= hi);
-                const float gap = fmaxf(fmaxf(lo - q2[0][k], q2[0][k] - hi), 0.f);
-                lb = fmaf(gap, gap, lb);
+                float dlo, dhi;
+                upk(sub2(pk(r[k], r[k]), box2[k]), dlo, dhi);             // {z - lo, z - hi}: one packed op, z in the scalar-broadcast form
+                float g;
+                asm("max.f32 %0, %1, %2, %3;" : "=f"(g) : "f"(-dlo), "f"(dhi), "f"(0.f));
+                lb = fmaf(g, g, lb);
             }
-            const bool need = alive && valid && !(lb + negm > CULL_MARGIN);
-            const unsigned bal = __ballot_sync(FULL, need);
-            if (lane == j) smask = bal;
+            if (on && !(lb + r[D] > CULL_MARGIN)) out |= 1u << i;
         }
-        // tile tests, one tile per lane (two super-boxes per pass), against the queries of the super-box's ballot only
+        return out;
+    };
+#pragma unroll 1
+    for (int c = 0; c < nchunk; c += 2) {
+        // chunk boxes, one query per lane, two chunks per round
+        const bool needA = alive && !(box_lb<D>(cbx + (size_t)c * 2 * D, q2[0]) + negm > CULL_MARGIN);
+        const bool needB = alive && c + 1 < nchunk && !(box_lb<D>(cbx + (size_t)(c + 1) * 2 * D, q2[0]) + negm > CULL_MARGIN);
+        const unsigned cmA = __ballot_sync(FULL, needA), cmB = __ballot_sync(FULL, needB);
+        if ((cmA | cmB) == 0u) continue;
+        // super-box tests, one SUPER-BOX per lane (lanes 0-15: chunk c, lanes 16-31: chunk c + 1) against the queries that
+        // need its chunk: lane j ends up with the mask of queries that need super-box j
+        unsigned smask;
+        {
+            const int sidx = (c + (lane >> 4)) * CG + (lane & 15);
+            u64 box2[D];
+            const bool ok = load_box(sbx + (size_t)(sidx < nsuper ? sidx : nsuper - 1) * 2 * D, sidx < nsuper, box2);
+            smask = test_box(box2, ok ? (lane < 16 ? cmA : cmB) : 0u);
+        }
+        // tile tests, one TILE per lane (two super-boxes per pass), against the queries of its super-box's mask
         unsigned act = __ballot_sync(FULL, smask != 0u);
         while (act) {
             const int ja = __ffs(act) - 1;
@@ -333,42 +376,12 @@ skb_plan_kernel(const __grid_constant__ ScoreLaunch L, const SparseLaunch* __res
             int jb = -1;
             if (act) { jb = __ffs(act) - 1; act &= act - 1u; }
             const int j = (lane < 16) ? ja : jb;
-            unsigned qm = __shfl_sync(FULL, smask, j < 0 ? 0 : j);
-            const int t = (s_base + (j < 0 ? 0 : j)) * SG + (lane & 15);
-            if (j < 0 || t >= ntiles) qm = 0u;
-            float lo[D], hi[D];
-            {
-                const int tc = t < ntiles ? t : ntiles - 1;
-                const float* b = bx + (size_t)tc * 2 * D;
-                if (D % 4 == 0) {
-#pragma unroll
-                    for (int k = 0; k < D; k += 4) {
-                        const float4 a = __ldg(reinterpret_cast<const float4*>(b + k));
-                        const float4 c = __ldg(reinterpret_cast<const float4*>(b + D + k));
-                        lo[k] = a.x; lo[k + 1] = a.y; lo[k + 2] = a.z; lo[k + 3] = a.w;
-                        hi[k] = c.x; hi[k + 1] = c.y; hi[k + 2] = c.z; hi[k + 3] = c.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < D; k++) { lo[k] = __ldg(b + k); hi[k] = __ldg(b + D + k); }
-                }
-            }
-            if (!(lo[0] <= hi[0])) qm = 0u;                               // tile without weight
-            unsigned tmask = 0u;
-            while (__any_sync(FULL, qm != 0u)) {
-                const bool on = qm != 0u;
-                const int i = on ? 31 - __clz(qm) : 0;
-                qm &= ~(1u << i);                                         // 0 stays 0
-                const float* qrow = rows + i * QS;
-                float lb = 0.f;
-#pragma unroll
-                for (int k = 0; k < D; k++) {
-                    const float zq = qrow[k];
-                    const float gap = fmaxf(fmaxf(lo[k] - zq, zq - hi[k]), 0.f);
-                    lb = fmaf(gap, gap, lb);
-                }
-                if (on && !(lb + qrow[D] > CULL_MARGIN)) tmask |= 1u << i;
-            }
+            const int jj = j < 0 ? 0 : j;
+            const unsigned qm = __shfl_sync(FULL, smask, jj);
+            const int t = ((c + (jj >> 4)) * CG + (jj & 15)) * SG + (lane & 15);
+            u64 box2[D];
+            const bool ok = load_box(bx + (size_t)(t < ntiles ? t : ntiles - 1) * 2 * D, j >= 0 && t < ntiles, box2);
+            const unsigned tmask = test_box(box2, ok ? qm : 0u);
             emit(tmask != 0u, (unsigned)t, tmask);
         }
     }
@@ -440,7 +453,7 @@ __global__ void __launch_bounds__(256) skb_scatter_kernel(const SparseLaunch* __
 // evaluate
 // ---------------------------------------------------------------------------------------------
 template <int D>
-__global__ void __launch_bounds__(32 * EVAL_WARPS, SKB_EVAL_MINB)
+__global__ void __launch_bounds__(32 * EVAL_WARPS, eval_minb(D))
 skb_eval_kernel(const SparseLaunch* __restrict__ SLp, unsigned nbuckets_pass, int redo)
 {
     constexpr int TN = tile_points(D);
@@ -473,9 +486,18 @@ skb_eval_kernel(const SparseLaunch* __restrict__ SLp, unsigned nbuckets_pass, in
         for (int h = 0; h < 2; h++) {
             const unsigned e = blk * EVAL_EB + h * 32 + lane;
             const bool in = e < n;
-            const unsigned m = in ? SL.srt_mask[e] : 0u;
-            s_tile[h * 32 + lane] = in ? SL.srt_tile[e] : 0xffffffffu;
-            s_warp[h * 32 + lane] = in ? SL.srt_warp[e] : 0u;
+            unsigned m = in ? SL.srt_mask[e] : 0u;
+            const unsigned tl = in ? SL.srt_tile[e] : 0xffffffffu;
+            const unsigned wp = in ? SL.srt_warp[e] : 0u;
+            if (redo && m) {                                              // second round: only the flagged queries of each entry
+                int jsel = 0;
+#pragma unroll 1
+                for (int j = 1; j < SL.njobs; j++)
+                    if (SL.sj[SL.jobs_of_group[j]].tile_base <= (int)tl) jsel = j;
+                m &= SL.sj[SL.jobs_of_group[jsel]].wflag[wp];
+            }
+            s_tile[h * 32 + lane] = tl;
+            s_warp[h * 32 + lane] = wp;
             s_mask[h * 32 + lane] = m;
             pc[h] = __popc(m);
         }
@@ -598,6 +620,7 @@ skb_eval_kernel(const SparseLaunch* __restrict__ SLp, unsigned nbuckets_pass, in
                             }
                             if (amin < NEWBEST_NONE) {
                                 atomicMin(reinterpret_cast<int*>(sj.newbest + qv[h]), __float_as_int(fmaxf(amin, 0.f)));
+                                atomicOr(sj.wflag + (qv[h] >> 5), 1u << (qv[h] & 31u));
                                 atomicAdd(SL.nflag, 1u);
                             } else {
                                 atomicExch(SL.overflow, 1u);               // NaN arithmetic on a finite row: fail loudly
@@ -698,7 +721,7 @@ static cudaError_t launch_group_d(const ScoreLaunch& L, int nl, const SparseLaun
                 skb_scatter_kernel<<<NB_CTAS, 256, hsmem, st>>>(SLd, (unsigned)b_lo, (unsigned)b_hi, redo);
                 count_launch(4);
             }
-            skb_eval_kernel<D><<<SKB_EVAL_MINB * sms, 32 * EVAL_WARPS, eval_smem, st>>>(SLd, (unsigned)nb, redo);
+            skb_eval_kernel<D><<<eval_minb(D) * sms, 32 * EVAL_WARPS, eval_smem, st>>>(SLd, (unsigned)nb, redo);
             count_launch();
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
         }
