@@ -38,7 +38,11 @@ constexpr float SUM_LIMIT = 1.6225928e32f;         // 2^107: a (query, tile) sum
 constexpr float NEWBEST_NONE = 3.0e38f;           // newbest[] holds 0x7f7f7f7f (3.39e38) until a query is flagged
 constexpr int PLAN_WARPS = 4;                     // warps per CTA of the plan kernel (independent of each other)
 constexpr int ENTRY_BLOCK = 256;                  // entries a plan warp reserves at a time (one global atomic per block)
-constexpr int EVAL_EB = 64;                       // sorted entries per evaluate work unit (two per lane)
+#ifndef SKB_EVAL_EPL
+#define SKB_EVAL_EPL 4
+#endif
+constexpr int EVAL_EPL = SKB_EVAL_EPL;            // sorted entries per lane of an evaluate work unit
+constexpr int EVAL_EB = 32 * EVAL_EPL;            // ... = entries per work unit: ~7 pairs each, i.e. ~14 full passes
 #ifndef SKB_EVAL_WARPS
 #define SKB_EVAL_WARPS 8
 #endif
@@ -322,7 +326,8 @@ skb_plan_kernel(const __grid_constant__ ScoreLaunch L, const SparseLaunch* __res
             for (int k = 0; k < D; k++) { lo[k] = __ldg(b + k); hi[k] = __ldg(b + D + k); }
         }
 #pragma unroll
-        for (int k = 0; k < D; k++) box2[k] = pk(lo[k], hi[k]);
+        for (int k = 0; k < D; k++)      // volatile: built once, kept in aligned register pairs (otherwise re-assembled per test)
+            asm volatile("mov.b64 %0, {%1, %2};" : "=l"(box2[k]) : "f"(lo[k]), "f"(hi[k]));
         return in_range && (lo[0] <= hi[0]);                              // (inf, -inf): a box without weight
     };
     // this lane's box against the queries of qm (walked highest bit first; the warp iterates until every lane is done)
@@ -410,7 +415,7 @@ __device__ __forceinline__ void entry_slice(const SparseLaunch& SL, unsigned& a,
     if (b > n) b = (unsigned)n;
 }
 
-__global__ void __launch_bounds__(256) skb_hist_kernel(const SparseLaunch* __restrict__ SLp, unsigned b_lo, unsigned b_hi, int redo)
+__global__ void __launch_bounds__(1024) skb_hist_kernel(const SparseLaunch* __restrict__ SLp, unsigned b_lo, unsigned b_hi, int redo)
 {
     extern __shared__ unsigned sh[];
     const SparseLaunch& SL = *SLp;
@@ -429,7 +434,7 @@ __global__ void __launch_bounds__(256) skb_hist_kernel(const SparseLaunch* __res
     if (blockIdx.x == 0 && threadIdx.x == 0) SL.hist[(size_t)nb * NB_CTAS] = 0u;      // the scan leaves the total here
 }
 
-__global__ void __launch_bounds__(256) skb_scatter_kernel(const SparseLaunch* __restrict__ SLp, unsigned b_lo, unsigned b_hi, int redo)
+__global__ void __launch_bounds__(1024) skb_scatter_kernel(const SparseLaunch* __restrict__ SLp, unsigned b_lo, unsigned b_hi, int redo)
 {
     extern __shared__ unsigned sh[];
     const SparseLaunch& SL = *SLp;
@@ -480,10 +485,10 @@ skb_eval_kernel(const SparseLaunch* __restrict__ SLp, unsigned nbuckets_pass, in
 #pragma unroll 1
     for (unsigned blk = gw; blk < nblk; blk += nw) {
         __syncwarp();
-        // ---- the block's 64 entries (two per lane) and the inclusive scan of their pair counts ----
-        unsigned pc[2];
+        // ---- the block's entries (EVAL_EPL per lane) and the inclusive scan of their pair counts ----
+        unsigned pc[EVAL_EPL];
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
+        for (int h = 0; h < EVAL_EPL; h++) {
             const unsigned e = blk * EVAL_EB + h * 32 + lane;
             const bool in = e < n;
             unsigned m = in ? SL.srt_mask[e] : 0u;
@@ -503,7 +508,7 @@ skb_eval_kernel(const SparseLaunch* __restrict__ SLp, unsigned nbuckets_pass, in
         }
         unsigned carry = 0u;
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
+        for (int h = 0; h < EVAL_EPL; h++) {
             unsigned incl = pc[h];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -526,9 +531,12 @@ skb_eval_kernel(const SparseLaunch* __restrict__ SLp, unsigned nbuckets_pass, in
             while (e_first < EVAL_EB && s_scan[e_first] <= r0) e_first++;
             const unsigned cur = s_tile[e_first];
             // last entry of this tile: entries are sorted, so compare each lane's entries with `cur`
-            const unsigned m0 = __ballot_sync(FULL, s_tile[lane] == cur);
-            const unsigned m1 = __ballot_sync(FULL, s_tile[32 + lane] == cur);
-            const int e_last = m1 ? 32 + (31 - __clz(m1)) : (31 - __clz(m0));
+            int e_last = e_first;
+#pragma unroll
+            for (int h = 0; h < EVAL_EPL; h++) {
+                const unsigned mh = __ballot_sync(FULL, s_tile[h * 32 + lane] == cur);
+                if (mh) e_last = h * 32 + (31 - __clz(mh));
+            }
             const unsigned r_end = s_scan[e_last];
 
             // which job, which tile
@@ -714,11 +722,11 @@ static cudaError_t launch_group_d(const ScoreLaunch& L, int nl, const SparseLaun
             const int nb = b_hi - b_lo;
             const size_t hsmem = (size_t)nb * 4;
             if (!redo || npass > 1) {
-                skb_hist_kernel<<<NB_CTAS, 256, hsmem, st>>>(SLd, (unsigned)b_lo, (unsigned)b_hi, redo);
+                skb_hist_kernel<<<NB_CTAS, 1024, hsmem, st>>>(SLd, (unsigned)b_lo, (unsigned)b_hi, redo);
                 // (the scan of a skipped histogram is harmless: round 1's evaluate returns before reading it)
                 size_t tb = scan_tmp_bytes;
                 if ((e = cub::DeviceScan::ExclusiveSum(scan_tmp, tb, SLh.hist, SLh.hist, nb * NB_CTAS + 1, st)) != cudaSuccess) return e;
-                skb_scatter_kernel<<<NB_CTAS, 256, hsmem, st>>>(SLd, (unsigned)b_lo, (unsigned)b_hi, redo);
+                skb_scatter_kernel<<<NB_CTAS, 1024, hsmem, st>>>(SLd, (unsigned)b_lo, (unsigned)b_hi, redo);
                 count_launch(4);
             }
             skb_eval_kernel<D><<<eval_minb(D) * sms, 32 * EVAL_WARPS, eval_smem, st>>>(SLd, (unsigned)nb, redo);
