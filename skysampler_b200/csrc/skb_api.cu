@@ -197,12 +197,24 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
         expected_group += nsplit[j];
     }
     const bool cull = cull_enabled();
-    const bool sparse = cull && g_opt_kernel.load(std::memory_order_relaxed) == 0;   // plan -> bucket -> evaluate -> finalize
+    // which culled kernel scores a job (a function of its dimension only, so that batching never changes the arithmetic):
+    // the sorted-incidence pipeline (plan -> bucket -> evaluate -> finalize) where it is the fastest (measured on B200,
+    // profiles/r02o_*: d = 3..7), round 1's lanes = queries kernel for d <= 2 (dense incidence, already at the SFU
+    // roofline of its pairs) and per-query kernel for d >= 8.  skb_set_option("kernel", 1 / 2) forces either family.
+    const int kopt = g_opt_kernel.load(std::memory_order_relaxed);
+    bool use_sparse[SKB_MAX_JOBS];
+    bool sparse = false;
+    for (int j = 0; j < n; j++) {
+        const int D = jobs[j].h->hk.D;
+        use_sparse[j] = cull && (kopt == 2 || (kopt == 0 && D >= 3 && D <= 7));
+        sparse |= use_sparse[j];
+    }
+    const bool fin_by_kernel = sparse && grouped;       // a group with a sparse member is finalized by the finalize kernel
     // finalize table
     for (int j = 0; j < n; j++) {
         const DevJob& dj = jobs[j];
         FinJob& fj = L.fin.fj[j];
-        const bool need_partial = !sparse && (grouped || nsplit[j] > 1);
+        const bool need_partial = !use_sparse[j] && (grouped || nsplit[j] > 1);
         if (need_partial) {
             void* p = nullptr;
             SKB_CUDA(ar.get(&p, (size_t)nsplit[j] * (size_t)dj.M * sizeof(double2)));
@@ -268,7 +280,8 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
         return cudaMemsetAsync(p, 0, nfb * sizeof(int), st);
     };
     int* group_counters = nullptr;
-    if (grouped && !sparse) SKB_CUDA(counters_for(jobs[0].M, &group_counters));
+    if (grouped && !(sparse && [&] { for (int j = 0; j < n; j++) if (!use_sparse[j]) return false; return true; }()))
+        SKB_CUDA(counters_for(jobs[0].M, &group_counters));
     unsigned long long* stats = nullptr;
     if (g_opt_stats.load(std::memory_order_relaxed)) {
         const int dev = jobs[0].h->device;
@@ -291,6 +304,9 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
             const DevJob& dj = jobs[j];
             const int D = dj.h->hk.D;
             const int qs = (D + 4) & ~3;
+            SLh.sj[j].M = dj.M;
+            SLh.sj[j].D = D;
+            if (!use_sparse[j]) continue;                // scored by a round-1 kernel: (m, S) partials instead of accumulators
             void* p = nullptr;
             SKB_CUDA(ar.get(&p, (size_t)dj.M * qs * sizeof(float)));
             SLh.sj[j].qz = reinterpret_cast<float*>(p);
@@ -360,7 +376,8 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
             sj.cols_identity = ident && ((reinterpret_cast<uintptr_t>(dj.q) & 15) == 0) && ((dj.ldq * esz) % 16 == 0);
             if (grouped) {
                 sj.fin_first = 0; sj.fin_count = n;
-                sj.counters = group_counters; sj.expected = expected_group;
+                sj.counters = group_counters;
+                sj.expected = fin_by_kernel ? 0x7fffffff : expected_group;    // nobody "arrives last": the finalize kernel does it
             } else {
                 sj.fin_first = j; sj.fin_count = 1;
                 if (nsplit[j] > 1) {
@@ -373,7 +390,7 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
             if (dj.h->hk.ntiles > max_ntiles) max_ntiles = dj.h->hk.ntiles;
         }
         if (max_rows <= 0) continue;
-        if (!sparse) {
+        if (!use_sparse[j0]) {
             SKB_CUDA(launch_score(D, !cull, L, nl, max_rows, max_split, max_ntiles, st));
             continue;
         }

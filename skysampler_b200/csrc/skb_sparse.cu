@@ -681,8 +681,13 @@ skb_sparse_fin_kernel(const __grid_constant__ ScoreLaunch L, const SparseLaunch*
     const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= Mj) return;
     const bool overflow = *SL.overflow != 0u;
+    if (count == 1 && SL.sj[f0].acc == nullptr) return;                    // that job finalized itself (round-1 kernel, ungrouped)
     finalize_query_with(L.fin, f0, count, v, [&](int f, long long vv, double& mstar, double& S) {
         const SparseJob& sj = SL.sj[f];
+        if (sj.acc == nullptr) {                                            // group member scored by a round-1 kernel
+            merge_partials(L.fin.fj[f].partial, L.fin.fj[f].nsplit, sj.M, vv, mstar, S);
+            return;
+        }
         const float negm = sj.qz[(size_t)vv * sj.qs + sj.D];
         const unsigned long long* a = sj.acc + (size_t)vv * ACC_LIMBS;
         // limbs are worth 2^-128, 2^-64, 1, 2^64: summed top down in fp64
