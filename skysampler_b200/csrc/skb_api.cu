@@ -598,7 +598,14 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
         }                                                                                      \
     } while (0)
 
+    // Every upload below goes through THIS stream: a synchronous cudaMemcpy from pageable memory may return before the DMA
+    // has landed, which only the legacy stream (not a non-blocking one) is ordered against.
     SKB_CUDA_C(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    SKB_CUDA_C(cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming));
+    SKB_CUDA_C(cudaEventRecord(ev0, 0));                     // device inputs produced on the legacy default stream (torch's
+    SKB_CUDA_C(cudaStreamWaitEvent(st, ev0, 0));             // default) are complete before the fit reads them
+    SKB_CUDA_C(cudaEventDestroy(ev0));
+    ev0 = nullptr;
     // ---- weights: validate, sum, max, sequential cumsum (host, fp64: numpy's own rounding) ----
     double wmax = 1.0;
     hk.sum_w = (double)N;
@@ -649,9 +656,9 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
     SKB_CUDA_C(cudaMalloc(&k->zt64, (size_t)N * d * sizeof(double)));
     if (w) {
         SKB_CUDA_C(cudaMalloc(&k->cumsum, (size_t)N * sizeof(double)));
-        SKB_CUDA_C(cudaMemcpy(k->cumsum, cs.data(), (size_t)N * 8, cudaMemcpyHostToDevice));
+        SKB_CUDA_C(cudaMemcpyAsync(k->cumsum, cs.data(), (size_t)N * 8, cudaMemcpyHostToDevice, st));
         SKB_CUDA_C(cudaMalloc(&d_w, (size_t)N * 8));
-        SKB_CUDA_C(cudaMemcpy(d_w, wh.data(), (size_t)N * 8, cudaMemcpyHostToDevice));
+        SKB_CUDA_C(cudaMemcpyAsync(d_w, wh.data(), (size_t)N * 8, cudaMemcpyHostToDevice, st));
     }
     const size_t tile_bytes = (size_t)hk.ntiles * stage_floats(d) * sizeof(float);
     SKB_CUDA_C(cudaMalloc(&k->tiles, tile_bytes));
@@ -666,14 +673,14 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
     hk.boxes = k->boxes;
     hk.sboxes = k->sboxes;
     hk.cboxes = cboxes;
-    SKB_CUDA_C(cudaMemcpy(k->dk, &hk, sizeof(KdeDev), cudaMemcpyHostToDevice));
+    SKB_CUDA_C(cudaMemcpyAsync(k->dk, &hk, sizeof(KdeDev), cudaMemcpyHostToDevice, st));
 
     const void* d_train = train;
     if (!is_device_ptr(train)) {
         const size_t esz = train_dtype == SKB_F32 ? 4 : 8;
         const size_t bytes = ((size_t)(N - 1) * ld_train + d) * esz;
         SKB_CUDA_C(cudaMalloc(&d_train_tmp, bytes));
-        SKB_CUDA_C(cudaMemcpy(d_train_tmp, train, bytes, cudaMemcpyHostToDevice));
+        SKB_CUDA_C(cudaMemcpyAsync(d_train_tmp, train, bytes, cudaMemcpyHostToDevice, st));
         d_train = d_train_tmp;
     }
     // ---- the fit proper, all on the device: whitened fp64 rows (original order: the draw centres) -> kd order of

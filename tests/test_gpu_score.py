@@ -288,10 +288,15 @@ def test_batched_shell_jobs_equal_individual_calls():
         jobs[j].q_is_whitened = 1; jobs[j].M = len(qs[j]); jobs[j].ldq = 4; jobs[j].cols = None
         jobs[j].out_logp = outs[j].data_ptr()
     before = _cabi.lib().skb_launch_count()
+    kdes[0].score_samples(qs[0])
+    torch.cuda.synchronize()
+    single = _cabi.lib().skb_launch_count() - before           # ordering (5 launches) + one pass of the score pipeline
+    before = _cabi.lib().skb_launch_count()
     _cabi.check(_cabi.lib().skb_score_batch(jobs, 5, None))
     torch.cuda.synchronize()
     delta = _cabi.lib().skb_launch_count() - before
-    assert delta <= 1 + 5 * 5 and (delta - 1) % 5 == 0       # ONE score launch for the five shells (+ 5 ordering launches per sorted table)
+    # ONE pass of the score pipeline for the five shells (+ 5 ordering launches per sorted table), not five
+    assert delta == (single - 5) + 5 * 5, (single, delta)
     for o, r in zip(outs, refs):
         assert np.array_equal(o.cpu().numpy(), r)
     for k in kdes:
