@@ -186,7 +186,7 @@ int skb_draw(skb_handle h, int64_t M, const double* u, const double* z,
 /*
  * Order-preserving stream compaction of accepted rows (`samples[inds]`, emulator.py:746-747).
  *   flags [M] uint8, rows [M][ld] (dtype), out [count][ld]; out_index [count] int64 source row
- *   ids (nullable); n_out HOST int64 receives the count (forces a sync).
+ *   ids (nullable); n_out receives the count: a HOST int64 (forces a sync) or a DEVICE int64 (the call stays asynchronous).
  */
 int skb_compact(const uint8_t* flags, int64_t M, const void* rows, int dtype, int64_t ld,
                 void* out, int64_t* out_index, int64_t* n_out, void* stream);

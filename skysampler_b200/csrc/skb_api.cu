@@ -767,7 +767,7 @@ static int score_one(skb_handle h, const void* q, int q_dtype, int64_t M, int64_
     // staged path: chunks of rows through device scratch, double buffered — the upload of chunk i+1 (copy stream)
     // overlaps the kernels of chunk i, and the download of chunk i is issued after the kernels of chunk i+1 are
     // queued, so that a blocking (pageable) download never leaves the GPU without work
-    const int64_t step = M > (1 << 20) ? HOST_STAGE_ROWS : M;
+    const int64_t step = M >= (1 << 20) ? HOST_STAGE_ROWS : M;
     const int64_t nchunks = (M + step - 1) / step;
     void* qbuf[2] = {nullptr, nullptr};
     double* obuf[2] = {nullptr, nullptr};
@@ -924,7 +924,7 @@ int skb_ratio_accept(const skb_handle* kdes, int n_kde, const int32_t* sign, con
         return SKB_OK;
     }
     // host buffers: chunks through device scratch with the copies on a side stream (see score_one)
-    const int64_t step = M > (1 << 20) ? HOST_STAGE_ROWS : M;
+    const int64_t step = M >= (1 << 20) ? HOST_STAGE_ROWS : M;
     const int64_t nchunks = (M + step - 1) / step;
     const int nbuf = nchunks > 1 ? 2 : 1;
     void* qbuf[2] = {nullptr, nullptr};
@@ -1095,8 +1095,13 @@ int skb_compact(const uint8_t* flags, int64_t M, const void* rows, int dtype, in
                 int64_t* out_index, int64_t* n_out, void* stream)
 {
     if (M < 0) return fail(SKB_EINVAL, "negative row count");
-    if (n_out) *n_out = 0;
-    if (M == 0) return SKB_OK;
+    const bool n_out_dev = n_out && is_device_ptr(n_out);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (n_out && !n_out_dev) *n_out = 0;
+    if (M == 0) {
+        if (n_out_dev) SKB_CUDA(cudaMemsetAsync(n_out, 0, 8, st));
+        return SKB_OK;
+    }
     if (!flags) return fail(SKB_EINVAL, "NULL flags");
     if (dtype != SKB_F64 && dtype != SKB_F32) return fail(SKB_EINVAL, "bad dtype %d", dtype);
     if ((rows == nullptr) != (out == nullptr)) return fail(SKB_EINVAL, "rows and out must be given together");
@@ -1104,17 +1109,20 @@ int skb_compact(const uint8_t* flags, int64_t M, const void* rows, int dtype, in
     const void* ptrs[] = {flags, rows, out, out_index};
     for (const void* p : ptrs)
         if (p && !is_device_ptr(p)) return fail(SKB_EINVAL, "skb_compact works on device buffers only");
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const long long nb = compact_nblocks(M);
     unsigned long long* ws = nullptr;
     SKB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), (size_t)(nb + 1) * 8, st));
     cudaError_t e = launch_compact(flags, M, rows, dtype == SKB_F32 ? 4 : 8, ld, out,
                                    reinterpret_cast<long long*>(out_index), ws, ws + nb, st);
     if (e == cudaSuccess && n_out) {
-        unsigned long long c = 0;
-        e = cudaMemcpyAsync(&c, ws + nb, 8, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        *n_out = (int64_t)c;
+        if (n_out_dev) {
+            e = cudaMemcpyAsync(n_out, ws + nb, 8, cudaMemcpyDeviceToDevice, st);       // stays asynchronous
+        } else {
+            unsigned long long c = 0;
+            e = cudaMemcpyAsync(&c, ws + nb, 8, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            *n_out = (int64_t)c;
+        }
     }
     cudaFreeAsync(ws, st);
     SKB_CUDA(e);

@@ -45,7 +45,8 @@ class RatioSampler(object):
         return t
 
     def score_accept(self, q, u, want_logp=False, want_ratio=False, stream=None):
-        """Device tensors in, device tensors out; asynchronous on ``stream`` (default: current)."""
+        """Device tensors in, device tensors out; asynchronous on ``stream`` (default: current).  The returned tensors are
+        buffers owned by this object: they are valid until the next call that produces the same output."""
         M, ld = q.shape
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
         accept = self._get("accept", (M,), torch.uint8)
@@ -57,15 +58,44 @@ class RatioSampler(object):
                                            ptr(logp), ptr(ratio), ptr(accept), ptr(in_band), stream_ptr(st)))
         return accept, in_band, logp, ratio
 
-    def compact(self, accept, rows, stream=None, sync_count=True):
-        """Accepted rows in input order (``samples[inds]``, emulator.py:746-747)."""
+    def compact(self, accept, rows, stream=None, sync_count=True, out=None, count_out=None):
+        """Accepted rows in input order (``samples[inds]``, emulator.py:746-747).
+
+        ``count_out``: a 1-element int64 CUDA tensor that receives the number of accepted rows without any host
+        synchronisation (the call stays asynchronous); otherwise ``sync_count=True`` returns it as a Python int."""
         M, ld = rows.shape
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
-        out = self._get("packed", (M, ld), rows.dtype)
+        if out is None:
+            out = self._get("packed", (M, ld), rows.dtype)
         cnt = C.c_int64(0)
+        if count_out is not None:
+            n_ptr = C.cast(C.c_void_p(count_out.data_ptr()), C.POINTER(C.c_int64))
+        else:
+            n_ptr = C.byref(cnt) if sync_count else None
         check(_cabi.lib().skb_compact(ptr(accept), M, ptr(rows), _cabi.dtype_code(rows), ld, ptr(out), None,
-                                      C.byref(cnt) if sync_count else None, stream_ptr(st)))
+                                      n_ptr, stream_ptr(st)))
         return out, int(cnt.value)
+
+    def draw(self, k, n, seed, offset=0, out=None, stream=None):
+        """``n`` Philox KDE draws from member ``k`` of the group straight into a device table (raw space when that KDE
+        carries an inverse whitening map) — the proposal step of the pipeline (emulator.py:530-544), asynchronous."""
+        kde = self.kdes[k]
+        if out is None:
+            out = self._get("draw%d" % k, (n, kde.ndim_), torch.float64)
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        check(_cabi.lib().skb_draw(kde._handle(), n, None, None, int(seed), int(offset), None, -1, 0.0, 0.0, 1, None,
+                                   ptr(out), kde.ndim_, None, None, None, stream_ptr(st)))
+        return out
+
+    def score_accept_host(self, q_host, u_host, accept_host, logp_host=None, stream=None):
+        """The C-ABI call with HOST buffers (numpy arrays or pinned torch tensors): rows + uniforms in, accept flags
+        (and optionally the log-densities) out; the library stages the copies itself.  Synchronous."""
+        M, ld = q_host.shape
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        check(_cabi.lib().skb_ratio_accept(self.handles, self.K, ptr(self.sign), ptr(self.log_abs_jac), self.log_m,
+                                           ptr(q_host), _cabi.dtype_code(q_host), M, ld, ptr(self.cols), ptr(u_host), self.band,
+                                           ptr(logp_host), None, ptr(accept_host), None, stream_ptr(st)))
+        return accept_host
 
     def step(self, q, u):
         """Device-resident batch: returns (accepted rows [n_acc, ld] view, n_acc)."""
@@ -102,7 +132,8 @@ class RatioSampler(object):
         side = getattr(self, "_side", None)
         if side is None:
             side = self._side = torch.cuda.Stream(device=self.device)
-        M, ld = batches[0][0].shape
+        M = max(b[0].shape[0] for b in batches)          # slots sized by the largest batch; shorter ones use a prefix
+        ld = batches[0][0].shape[1]
         slots = []
         for s in range(2):
             slots.append((self._get("q_pipe%d" % s, (M, ld), batches[0][0].dtype), self._get("u_pipe%d" % s, (M,), torch.float64),
@@ -122,8 +153,9 @@ class RatioSampler(object):
             with torch.cuda.stream(side):
                 if i >= 2:
                     side.wait_event(free[i % 2])              # the kernels of batch i-2 are done with this slot
-                qd.copy_(batches[i][0], non_blocking=True)
-                ud.copy_(batches[i][1], non_blocking=True)
+                m_i = batches[i][0].shape[0]
+                qd[:m_i].copy_(batches[i][0], non_blocking=True)
+                ud[:m_i].copy_(batches[i][1], non_blocking=True)
                 ready[i % 2].record(side)
 
         trace = [] if os.environ.get("SKB_TRACE_RUN_HOST") else None      # debug: per-batch device timeline on stderr
@@ -143,6 +175,8 @@ class RatioSampler(object):
             main.wait_event(ready[i % 2])
             if trace is not None:
                 trace[-1][1].record(main)
+            m_i = batches[i][0].shape[0]
+            qd, ud, keep = qd[:m_i], ud[:m_i], keep[:m_i]
             accept, _, _, _ = self.score_accept(qd, ud, stream=main)
             if trace is not None:
                 trace[-1][2].record(main)
@@ -151,7 +185,7 @@ class RatioSampler(object):
             keep.copy_(accept)
             self.compact(keep, qd, stream=main, sync_count=False)
             free[i % 2].record(main)
-            flags_host[i].copy_(keep, non_blocking=True)
+            flags_host[i][:m_i].copy_(keep, non_blocking=True)
             counts_host[i:i + 1].copy_(keep.sum(dtype=torch.int64).reshape(1), non_blocking=True)
         main.synchronize()
         if trace is not None:

@@ -487,3 +487,21 @@ def test_pq_forced_training_splits_merge_to_the_same_answer():
     assert np.abs(one - five)[near].max() <= 2e-5
     _check(five[:300], brute64.score(z, None, 0.1, q[:300]))
     kde.close()
+
+
+def test_refits_on_recycled_memory_give_the_same_answer():
+    """Fit -> score -> drop, four times over: later fits run on recycled device memory and on their own stream.  (A
+    synchronous copy from pageable memory is only ordered against the legacy stream; a fit stream that did not issue
+    its own uploads once read training rows that had not landed yet — on every fit after the first.)"""
+    rs = np.random.RandomState(20000)
+    z = rs.normal(size=(20000, 8)); q = 1.2 * rs.normal(size=(777, 8))
+    w = rs.uniform(0.5, 2.0, 20000)
+    ref = brute64.score(z, w, 0.4, q)
+    first = None
+    for rep in range(4):
+        kde = _kde(z, w, 0.4)
+        got = kde.score_samples(q)
+        kde.close()
+        _check(got, ref)
+        first = got if first is None else first
+        assert np.array_equal(got, first), rep
