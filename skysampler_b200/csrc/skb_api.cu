@@ -206,7 +206,9 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
     bool sparse = false;
     for (int j = 0; j < n; j++) {
         const int D = jobs[j].h->hk.D;
-        use_sparse[j] = cull && (kopt == 2 || (kopt == 0 && D >= 3 && D <= 7));
+        // (small training sets — up to two chunks of tiles — stay on the single-launch round-1 kernels: the pipeline's
+        //  fixed cost of a dozen launches would dominate; like D, the tile count is a property of the fitted KDE)
+        use_sparse[j] = cull && (kopt == 2 || (kopt == 0 && D >= 3 && D <= 7 && jobs[j].h->hk.ntiles > 2 * CG * SG));
         sparse |= use_sparse[j];
     }
     const bool fin_by_kernel = sparse && grouped;       // a group with a sparse member is finalized by the finalize kernel
