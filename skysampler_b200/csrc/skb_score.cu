@@ -463,20 +463,7 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
     mref[0] = 0.f; S[0] = 0.0; nm2[0] = 0.f;
     const float ref_bias = kde->ref_bias;
     const float PQ_LIMIT = exp2f((float)SKB_PQ_SLACK - ref_bias);     // a lane term this large re-centres
-    {
-        // exponent reference, one query at a time with the whole warp on it (lanes = boxes, then lanes = points)
-        const long long vlast = M - qbase;                              // rows of this warp that exist
-#pragma unroll 1
-        for (int src = 0; src < 32; src++) {
-            float zq[D];
-#pragma unroll
-            for (int k = 0; k < D; k++) zq[k] = __shfl_sync(FULL, q2[0][k], src);
-            float best = ref_bias;
-            if (src < vlast) best = coop_home_reference<D>(kde, ntiles, zq, lane);
-            if (!(best < 1.0e30f)) best = ref_bias;                      // inf / NaN rows (or padding only): finite reference
-            if (lane == src) { bmin[0] = best; mref[0] = floorf(best) - ref_bias; nm2[0] = -mref[0]; }
-        }
-    }
+    home_reference<D, Q>(kde, ntiles, q2, bmin, mref, nm2);
 
 #pragma unroll
     for (int k = 0; k < D; k++) rows[lane * QS + k] = q2[0][k];

@@ -578,113 +578,6 @@ __device__ __forceinline__ void home_reference(const KdeDev* __restrict__ kde, i
     }
 }
 
-// ---- warp-cooperative reference search (lanes = boxes / points), used by the plan kernel and the per-query kernel ----
-template <int D>
-__device__ __forceinline__ float box_lb(const float* __restrict__ b, const float (&zq)[D])
-{
-    float lb = 0.f;
-#pragma unroll
-    for (int k = 0; k < D; k++) {
-        const float lo = __ldg(b + k), hi = __ldg(b + D + k);
-        const float gap = fmaxf(fmaxf(lo - zq[k], zq[k] - hi), 0.f);      // empty boxes are (inf, -inf): gap = inf
-        lb = fmaf(gap, gap, lb);
-    }
-    return lb;
-}
-
-// min over a tile of the weighted exponent |c dz|^2 - log2 w, lanes = points (warp cooperative, warp-uniform result)
-template <int D>
-__device__ __forceinline__ float coop_scan_tile(const float* __restrict__ tile, const float (&zq)[D], bool has_w, int lane)
-{
-    constexpr int TN = tile_points(D);
-    float b = INFINITY;
-#pragma unroll
-    for (int p = lane; p < TN; p += 32) {
-        float a = has_w ? fminf(-__log2f(__ldg(tile + D * TN + p)), LW_CAP) : 0.f;
-#pragma unroll
-        for (int k = 0; k < D; k++) {
-            const float d = zq[k] - __ldg(tile + k * TN + p);
-            a = fmaf(d, d, a);
-        }
-        b = fminf(b, a);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) b = fminf(b, __shfl_xor_sync(0xffffffffu, b, o));
-    return b;
-}
-
-// (value, index) argmin over the warp; ties keep the smaller index; result is warp uniform
-__device__ __forceinline__ void warp_argmin(float& v, int& i)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, i, o);
-        if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
-    }
-}
-
-// Exponent reference of ONE query (coordinates broadcast to the warp), warp cooperative with lanes = boxes / points:
-//   (1) the super-box nearest to the query by box distance (exact branch and bound over chunk boxes -> super-boxes): "home";
-//   (2) its tiles are scanned in order of box distance for the smallest weighted exponent |c dz|^2 - log2 w, as long as a
-//       tile's box can still beat the best point found.
-// A real point's exponent is an upper bound of the true minimum, which is all the window needs for accuracy; a tight
-// one (the nearest neighbour usually lives in the home super-box) is what lets the box tests cull.  Should a point far
-// below it turn up later, the evaluate step detects the overflow and the query is re-referenced exactly (see there).
-template <int D>
-__device__ __forceinline__ float coop_home_reference(const KdeDev* __restrict__ kde, int ntiles, const float (&zq)[D], int lane)
-{
-    constexpr unsigned FULL = 0xffffffffu;
-    const bool has_w = kde->has_w != 0;
-    const int nchunk = kde->nchunk, nsuper = kde->nsuper;
-    // nearest chunk box
-    float cb = INFINITY;
-    int ci = 0;
-#pragma unroll 1
-    for (int c0 = 0; c0 < nchunk; c0 += 32) {
-        const int c = c0 + lane;
-        const float lb = c < nchunk ? box_lb<D>(kde->cboxes + (size_t)c * 2 * D, zq) : INFINITY;
-        if (lb < cb) { cb = lb; ci = c; }
-    }
-    warp_argmin(cb, ci);
-    // nearest super-box: the nearest chunk's first, then every chunk whose box is closer than the best super-box so far
-    float sb = INFINITY;
-    int si = ci * CG;
-    auto scan_chunk = [&](int c) {
-        const int s = c * CG + (lane & 15);
-        float lb = (lane < CG && s < nsuper) ? box_lb<D>(kde->sboxes + (size_t)s * 2 * D, zq) : INFINITY;
-        int idx = s;
-        warp_argmin(lb, idx);
-        if (lb < sb) { sb = lb; si = idx; }
-    };
-    scan_chunk(ci);
-#pragma unroll 1
-    for (int c0 = 0; c0 < nchunk; c0 += 32) {
-        const int c = c0 + lane;
-        const float lb = (c < nchunk && c != ci) ? box_lb<D>(kde->cboxes + (size_t)c * 2 * D, zq) : INFINITY;
-        unsigned m = __ballot_sync(FULL, lb < sb);
-        while (m) {
-            const int cc = c0 + __ffs(m) - 1;
-            m &= m - 1u;
-            scan_chunk(cc);
-        }
-    }
-    // tiles of the home super-box, nearest box first
-    const int t = si * SG + (lane & 15);
-    const float lbt = (lane < SG && t < ntiles) ? box_lb<D>(kde->boxes + (size_t)t * 2 * D, zq) : INFINITY;
-    float best = INFINITY;
-    unsigned todo = __ballot_sync(FULL, lbt < INFINITY);
-    while (todo) {
-        float v = ((todo >> lane) & 1u) ? lbt : INFINITY;
-        int l = lane;
-        warp_argmin(v, l);
-        if (!(v < best)) break;
-        todo &= ~(1u << l);
-        best = fminf(best, coop_scan_tile<D>(kde->tiles + (size_t)(si * SG + (l & 15)) * stage_floats(D), zq, has_w, lane));
-    }
-    return best;
-}
-
 // ---- epilogue: finalize from registers, or publish the partial state and let the last-arriving CTA of a
 // finalize block merge splits / form the ratio + accept ----
 template <int D, int Q, int NTH = NT>
