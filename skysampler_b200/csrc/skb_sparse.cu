@@ -326,8 +326,7 @@ skb_plan_kernel(const __grid_constant__ ScoreLaunch L, const SparseLaunch* __res
             for (int k = 0; k < D; k++) { lo[k] = __ldg(b + k); hi[k] = __ldg(b + D + k); }
         }
 #pragma unroll
-        for (int k = 0; k < D; k++)      // volatile: built once, kept in aligned register pairs (otherwise re-assembled per test)
-            asm volatile("mov.b64 %0, {%1, %2};" : "=l"(box2[k]) : "f"(lo[k]), "f"(hi[k]));
+        for (int k = 0; k < D; k++) box2[k] = pk(lo[k], hi[k]);
         return in_range && (lo[0] <= hi[0]);                              // (inf, -inf): a box without weight
     };
     // this lane's box against the queries of qm (walked highest bit first; the warp iterates until every lane is done)
@@ -347,11 +346,11 @@ skb_plan_kernel(const __grid_constant__ ScoreLaunch L, const SparseLaunch* __res
             float lb = 0.f;
 #pragma unroll
             for (int k = 0; k < D; k++) {
-                float dlo, dhi;
-                upk(sub2(pk(r[k], r[k]), box2[k]), dlo, dhi);             // {z - lo, z - hi}: one packed op, z in the scalar-broadcast form
-                float g;
-                asm("max.f32 %0, %1, %2, %3;" : "=f"(g) : "f"(-dlo), "f"(dhi), "f"(0.f));
-                lb = fmaf(g, g, lb);
+                // (a packed {z - lo, z - hi} costs more than it saves here: the result pair has to be moved around)
+                float blo, bhi;
+                upk(box2[k], blo, bhi);
+                const float gap = fmaxf(fmaxf(blo - r[k], r[k] - bhi), 0.f);
+                lb = fmaf(gap, gap, lb);
             }
             if (on && !(lb + r[D] > CULL_MARGIN)) out |= 1u << i;
         }
