@@ -769,7 +769,7 @@ static int score_one(skb_handle h, const void* q, int q_dtype, int64_t M, int64_
     // staged path: chunks of rows through device scratch, double buffered — the upload of chunk i+1 (copy stream)
     // overlaps the kernels of chunk i, and the download of chunk i is issued after the kernels of chunk i+1 are
     // queued, so that a blocking (pageable) download never leaves the GPU without work
-    const int64_t step = M >= (1 << 20) ? HOST_STAGE_ROWS : M;
+    const int64_t step = M > (1 << 21) ? HOST_STAGE_ROWS : M;       // up to 2^21 rows: one chunk (one ordering pass, one launch set)
     const int64_t nchunks = (M + step - 1) / step;
     void* qbuf[2] = {nullptr, nullptr};
     double* obuf[2] = {nullptr, nullptr};
@@ -926,7 +926,7 @@ int skb_ratio_accept(const skb_handle* kdes, int n_kde, const int32_t* sign, con
         return SKB_OK;
     }
     // host buffers: chunks through device scratch with the copies on a side stream (see score_one)
-    const int64_t step = M >= (1 << 20) ? HOST_STAGE_ROWS : M;
+    const int64_t step = M > (1 << 21) ? HOST_STAGE_ROWS : M;       // up to 2^21 rows: one chunk (one ordering pass, one launch set)
     const int64_t nchunks = (M + step - 1) / step;
     const int nbuf = nchunks > 1 ? 2 : 1;
     void* qbuf[2] = {nullptr, nullptr};

@@ -42,8 +42,10 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, fl
     n0 = rad * c; n1 = rad * s;
 }
 
+// D is a template parameter: the per-draw vectors live in registers (with a run-time D they were local-memory arrays).
+template <int D>
 __global__ void __launch_bounds__(256)
-skb_draw_kernel(const KdeDev* __restrict__ kde, int D, long long M,
+skb_draw_kernel(const KdeDev* __restrict__ kde, long long M,
                 const double* __restrict__ u_in, const double* __restrict__ z_in,
                 uint64_t seed, uint64_t offset, const long long* __restrict__ rows,
                 int rcol, double rmin, double rmax, int max_attempts,
@@ -57,11 +59,12 @@ skb_draw_kernel(const KdeDev* __restrict__ kde, int D, long long M,
     const double* __restrict__ cs = kde->cumsum_w;
     const double h = kde->h;
     const bool streams = (u_in != nullptr);
+    const bool has_winv = kde->has_winv != 0;
     const uint64_t cidx = (uint64_t)i + offset;
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
 
     long long idx = 0;
-    double zs[SKB_MAXD], x[SKB_MAXD];
+    double zs[D], x[D];
     bool bad = false;
     const int nattempt = streams ? 1 : (max_attempts > 0 ? max_attempts : 1);
     for (int attempt = 0; attempt < nattempt; attempt++) {
@@ -74,11 +77,11 @@ skb_draw_kernel(const KdeDev* __restrict__ kde, int D, long long M,
         }
         if (cs) {
             // np.searchsorted(cumsum_weight, u * sum_weight)  (side='left')   sklearn _kde.py:345-347
-            const double target = u * cs[N - 1];
+            const double target = u * __ldg(cs + N - 1);
             long long lo = 0, hi = N;
             while (lo < hi) {
                 const long long mid = (lo + hi) >> 1;
-                if (cs[mid] < target) lo = mid + 1; else hi = mid;
+                if (__ldg(cs + mid) < target) lo = mid + 1; else hi = mid;
             }
             idx = lo < N ? lo : N - 1;
         } else {
@@ -87,33 +90,57 @@ skb_draw_kernel(const KdeDev* __restrict__ kde, int D, long long M,
         }
         const double* __restrict__ ctr = kde->zt64 + idx * D;
         if (streams) {
-            for (int k = 0; k < D; k++) zs[k] = __dadd_rn(ctr[k], __dmul_rn(h, z_in[i * D + k]));   // rng.normal(data[i], h): loc + scale*g, two roundings like numpy
+#pragma unroll
+            for (int k = 0; k < D; k++) zs[k] = __dadd_rn(__ldg(ctr + k), __dmul_rn(h, z_in[i * D + k]));   // rng.normal(data[i], h): loc + scale*g, two roundings like numpy
         } else {
+#pragma unroll
             for (int k = 0; k < D; k += 4) {
                 const uint4 r = philox4x32_10(make_uint4((uint32_t)cidx, (uint32_t)(cidx >> 32), (uint32_t)attempt,
                                                          1u + (uint32_t)(k >> 2)), key);
                 float n[4];
                 box_muller(r.x, r.y, n[0], n[1]);
                 box_muller(r.z, r.w, n[2], n[3]);
-                for (int t = 0; t < 4 && k + t < D; t++) zs[k + t] = ctr[k + t] + h * (double)n[t];
+#pragma unroll
+                for (int t = 0; t < 4; t++)
+                    if (k + t < D) zs[k + t] = __ldg(ctr + k + t) + h * (double)n[t];
             }
         }
-        if (kde->has_winv) {
+        if (has_winv) {
+#pragma unroll
             for (int c = 0; c < D; c++) {
                 double a = 0.0;
+#pragma unroll
                 for (int k = 0; k < D; k++) a = fma(zs[k], kde->Winv[k * D + c], a);
                 x[c] = a + kde->mu[c];
             }
         } else {
+#pragma unroll
             for (int c = 0; c < D; c++) x[c] = zs[c];
         }
-        bad = (rcol >= 0) && ((x[rcol] > rmax) || (x[rcol] < rmin));   // emulator.py:370
+        bad = false;
+        if (rcol >= 0) {
+            double xr = x[0];
+#pragma unroll
+            for (int c = 1; c < D; c++) xr = (c == rcol) ? x[c] : xr;
+            bad = (xr > rmax) || (xr < rmin);                          // emulator.py:370
+        }
         if (!bad) break;
     }
     const long long o = rows ? rows[i] : i;
     if (out_idx) out_idx[o] = idx;
-    if (out_x) for (int c = 0; c < D; c++) out_x[o * ld_out + c] = x[c];
-    if (out_z) for (int k = 0; k < D; k++) out_z[o * D + k] = zs[k];
+    if (out_x) {
+        if ((D % 2 == 0) && ((ld_out & 1) == 0) && ((reinterpret_cast<uintptr_t>(out_x) & 15) == 0)) {
+#pragma unroll
+            for (int c = 0; c < D; c += 2) *reinterpret_cast<double2*>(out_x + o * ld_out + c) = make_double2(x[c], x[c + 1]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < D; c++) out_x[o * ld_out + c] = x[c];
+        }
+    }
+    if (out_z) {
+#pragma unroll
+        for (int k = 0; k < D; k++) out_z[o * D + k] = zs[k];
+    }
     if (out_flag) out_flag[o] = bad ? 1 : 0;
     if (n_flagged) {
         const unsigned ballot = __ballot_sync(__activemask(), bad);
@@ -129,9 +156,15 @@ cudaError_t launch_draw(const KdeDev* kde, int D, long long M, const double* u, 
 {
     if (M <= 0) return cudaSuccess;
     const int bs = 256;
-    skb_draw_kernel<<<(unsigned)((M + bs - 1) / bs), bs, 0, st>>>(kde, D, M, u, z, seed, offset, rows, rcol, rmin,
-                                                                 rmax, max_attempts, out_idx, out_x, ld_out, out_z,
-                                                                 out_flag, n_flagged);
+    const unsigned grid = (unsigned)((M + bs - 1) / bs);
+    switch (D) {
+#define SKB_CASE(d) case d: skb_draw_kernel<d><<<grid, bs, 0, st>>>(kde, M, u, z, seed, offset, rows, rcol, rmin, rmax, max_attempts, \
+                                                                  out_idx, out_x, ld_out, out_z, out_flag, n_flagged); break;
+        SKB_CASE(1) SKB_CASE(2) SKB_CASE(3) SKB_CASE(4) SKB_CASE(5) SKB_CASE(6) SKB_CASE(7) SKB_CASE(8)
+        SKB_CASE(9) SKB_CASE(10) SKB_CASE(11) SKB_CASE(12) SKB_CASE(13) SKB_CASE(14) SKB_CASE(15) SKB_CASE(16)
+#undef SKB_CASE
+        default: return cudaErrorInvalidValue;
+    }
     count_launch();
     return cudaGetLastError();
 }
@@ -214,10 +247,12 @@ compact_scatter_kernel(const unsigned char* __restrict__ flags, long long M, con
                        int row_bytes, unsigned char* __restrict__ out, long long* __restrict__ out_index,
                        const unsigned long long* __restrict__ offsets)
 {
-    const long long base = (long long)blockIdx.x * CP_CHUNK + (long long)threadIdx.x * CP_PER_THREAD;
+    const long long cbase = (long long)blockIdx.x * CP_CHUNK;
+    const long long base = cbase + (long long)threadIdx.x * CP_PER_THREAD;
     const unsigned m = base < M ? load_flags8(flags, base, M) : 0u;
     const int c = __popc(m);
     __shared__ int wsum[CP_THREADS / 32];
+    __shared__ unsigned short sel[CP_CHUNK];             // accepted rows of this chunk (offset in the chunk), in input order
     int incl = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -226,25 +261,33 @@ compact_scatter_kernel(const unsigned char* __restrict__ flags, long long M, con
     }
     if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
     __syncthreads();
-    int wbase = 0;
-    for (int w = 0; w < (int)(threadIdx.x >> 5); w++) wbase += wsum[w];
-    unsigned long long dst = offsets[blockIdx.x] + (unsigned long long)(wbase + incl - c);
-    for (int t = 0; t < 8; t++) {
-        if (!((m >> t) & 1u)) continue;
-        const long long src = base + t;
-        if (out_index) out_index[dst] = src;
-        if (out) {
-            const unsigned char* s = rows + (size_t)src * row_bytes;
-            unsigned char* d = out + (size_t)dst * row_bytes;
-            if ((row_bytes & 15) == 0 && ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 15) == 0) {
-                for (int b = 0; b < row_bytes; b += 16) *reinterpret_cast<uint4*>(d + b) = *reinterpret_cast<const uint4*>(s + b);
-            } else if ((row_bytes & 3) == 0 && ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 3) == 0) {
-                for (int b = 0; b < row_bytes; b += 4) *reinterpret_cast<unsigned*>(d + b) = *reinterpret_cast<const unsigned*>(s + b);
-            } else {
-                for (int b = 0; b < row_bytes; b++) d[b] = s[b];
-            }
-        }
-        dst++;
+    int wbase = 0, total = 0;
+    for (int w = 0; w < CP_THREADS / 32; w++) {
+        if (w < (int)(threadIdx.x >> 5)) wbase += wsum[w];
+        total += wsum[w];
+    }
+    int pos = wbase + incl - c;
+    for (int t = 0; t < 8; t++)
+        if ((m >> t) & 1u) sel[pos++] = (unsigned short)(threadIdx.x * CP_PER_THREAD + t);
+    __syncthreads();
+    const unsigned long long dst0 = offsets[blockIdx.x];
+    if (out_index)
+        for (int r = threadIdx.x; r < total; r += CP_THREADS) out_index[dst0 + r] = cbase + sel[r];
+    if (!out) return;
+    // the whole CTA copies the accepted rows: consecutive threads move consecutive 16-byte (or 4- / 1-byte) pieces, so the
+    // writes are fully coalesced and the reads are coalesced within each row
+    const bool a16 = (row_bytes & 15) == 0 && ((reinterpret_cast<uintptr_t>(rows) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    const bool a4 = (row_bytes & 3) == 0 && ((reinterpret_cast<uintptr_t>(rows) | reinterpret_cast<uintptr_t>(out)) & 3) == 0;
+    const int unit = a16 ? 16 : (a4 ? 4 : 1);
+    const int upr = row_bytes / unit;
+    const long long nunits = (long long)total * upr;
+    for (long long i = threadIdx.x; i < nunits; i += CP_THREADS) {
+        const int r = (int)(i / upr), part = (int)(i % upr);
+        const unsigned char* sp = rows + (size_t)(cbase + sel[r]) * row_bytes + (size_t)part * unit;
+        unsigned char* dp = out + (size_t)(dst0 + r) * row_bytes + (size_t)part * unit;
+        if (a16) *reinterpret_cast<uint4*>(dp) = *reinterpret_cast<const uint4*>(sp);
+        else if (a4) *reinterpret_cast<unsigned*>(dp) = *reinterpret_cast<const unsigned*>(sp);
+        else *dp = *sp;
     }
 }
 

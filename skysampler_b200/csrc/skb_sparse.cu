@@ -53,6 +53,9 @@ constexpr int EVAL_EB = 32 * EVAL_EPL;            // ... = entries per work unit
 #define SKB_EVAL_MINB_HI 2      // ... and above
 #endif
 __host__ __device__ constexpr int eval_minb(int D) { return D <= 8 ? SKB_EVAL_MINB_LO : SKB_EVAL_MINB_HI; }
+#ifndef SKB_EVAL_STEP8
+#define SKB_EVAL_STEP8 8        // > 0: 8 points per inner step (eight independent FMA chains per lane) up to this dimension
+#endif
 constexpr int EVAL_WARPS = SKB_EVAL_WARPS;
 constexpr int NB_CTAS = 128;                      // CTAs of the bucket kernels (slices of the entry list)
 constexpr int MAX_BUCKETS = 48 * 1024;            // tiles per bucket pass (shared-memory histogram)
@@ -597,11 +600,19 @@ skb_eval_kernel(const SparseLaunch* __restrict__ SLp, unsigned nbuckets_pass, in
                     float unused[2];
                     sum2[0] = pk(0.f, 0.f);
                     sum2[1] = pk(0.f, 0.f);
+#if SKB_EVAL_STEP8
+                    if constexpr (D <= SKB_EVAL_STEP8) {
 #pragma unroll 1
-                    for (int pt = 0; pt < TN; pt += 4) {
-                        StepOperands<D> A;
-                        A.template load<true>(slot, pt);
-                        step_compute<D, 2, false, false>(A, qq, nm, sum2, unused);
+                        for (int pt = 0; pt < TN; pt += 8) step_compute8<D, 2, false>(slot, pt, qq, nm, sum2, unused);
+                    } else
+#endif
+                    {
+#pragma unroll 1
+                        for (int pt = 0; pt < TN; pt += 4) {
+                            StepOperands<D> A;
+                            A.template load<true>(slot, pt);
+                            step_compute<D, 2, false, false>(A, qq, nm, sum2, unused);
+                        }
                     }
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
