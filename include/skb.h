@@ -142,6 +142,9 @@ int skb_score_batch(const skb_job* jobs, int n_jobs, void* stream);
  *     log_ratio = sum_k sign[k] * (log p_k + log_abs_jac[k]) - log_m
  *     accept[i] = log(u[i]) < log_ratio          (u < p_ref / (m * prod p_proposal))
  *     in_band[i] = |log_ratio - log(u[i])| <= band     (knife-edge flag for parity checks)
+ *   The test runs in LOG space; the reference compares in linear space (exp of each log-density), where a log-density
+ *   below -745 underflows to 0 and turns the ratio into 0/0 = NaN (reject) or x/0 = inf (accept).  Rows that deep in the
+ *   tails can therefore decide differently; they are not flagged by in_band (out_logp shows them).
  *   sign[k] = +1 for reference-density terms (wcr), -1 for proposal terms (dc, wr).
  *   cols    [n_kde][SKB_MAXD] HOST int32 column indices into the proposal table (-1 padded), or NULL.
  *   u       [M] uniforms (fp64) or NULL -> no accept test, only log p's.

@@ -101,6 +101,7 @@ struct skb_kde {
     int sms = 148;
     KdeDev hk;                 // host copy of the device descriptor
     KdeDev* dk = nullptr;      // device descriptor
+    void* slab = nullptr;      // the one device allocation everything below lives in
     float* tiles = nullptr;
     float* boxes = nullptr;
     float* sboxes = nullptr;
@@ -581,10 +582,14 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
     int* d_perm = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     auto cleanup = [&](int code) {
-        if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
-        if (d_train_tmp) cudaFree(d_train_tmp);
-        if (d_w) cudaFree(d_w);
-        if (d_perm) cudaFree(d_perm);
+        if (st) {
+            // fit-time temporaries come from the stream-ordered pool (cudaFree would synchronise the device three times)
+            if (d_train_tmp) cudaFreeAsync(d_train_tmp, st);
+            if (d_w) cudaFreeAsync(d_w, st);
+            if (d_perm) cudaFreeAsync(d_perm, st);
+            cudaStreamSynchronize(st);
+            cudaStreamDestroy(st);
+        }
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (code != SKB_OK) { skb_destroy(k); }
@@ -654,21 +659,33 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
         hk.ref_bias = 90.f - (float)extra;
     }
 
-    // ---- device buffers ----
-    SKB_CUDA_C(cudaMalloc(&k->zt64, (size_t)N * d * sizeof(double)));
+    // ---- device buffers: one slab per handle (one allocation, one free) ----
+    const size_t tile_bytes = (size_t)hk.ntiles * stage_floats(d) * sizeof(float);
+    {
+        size_t off = 0;
+        auto carve = [&off](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+        const size_t o_zt = carve((size_t)N * d * sizeof(double));
+        const size_t o_cs = carve(w ? (size_t)N * sizeof(double) : 0);
+        const size_t o_tiles = carve(tile_bytes);
+        const size_t o_boxes = carve((size_t)hk.ntiles * 2 * d * sizeof(float));
+        const size_t o_sb = carve((size_t)(hk.nsuper + hk.nchunk) * 2 * d * sizeof(float));   // super-boxes, then chunk boxes
+        const size_t o_dk = carve(sizeof(KdeDev));
+        SKB_CUDA_C(cudaMalloc(&k->slab, off));
+        char* base = reinterpret_cast<char*>(k->slab);
+        k->zt64 = reinterpret_cast<double*>(base + o_zt);
+        k->cumsum = w ? reinterpret_cast<double*>(base + o_cs) : nullptr;
+        k->tiles = reinterpret_cast<float*>(base + o_tiles);
+        k->boxes = reinterpret_cast<float*>(base + o_boxes);
+        k->sboxes = reinterpret_cast<float*>(base + o_sb);
+        k->dk = reinterpret_cast<KdeDev*>(base + o_dk);
+    }
     if (w) {
-        SKB_CUDA_C(cudaMalloc(&k->cumsum, (size_t)N * sizeof(double)));
         SKB_CUDA_C(cudaMemcpyAsync(k->cumsum, cs.data(), (size_t)N * 8, cudaMemcpyHostToDevice, st));
-        SKB_CUDA_C(cudaMalloc(&d_w, (size_t)N * 8));
+        SKB_CUDA_C(cudaMallocAsync(reinterpret_cast<void**>(&d_w), (size_t)N * 8, st));
         SKB_CUDA_C(cudaMemcpyAsync(d_w, wh.data(), (size_t)N * 8, cudaMemcpyHostToDevice, st));
     }
-    const size_t tile_bytes = (size_t)hk.ntiles * stage_floats(d) * sizeof(float);
-    SKB_CUDA_C(cudaMalloc(&k->tiles, tile_bytes));
-    SKB_CUDA_C(cudaMalloc(&k->boxes, (size_t)hk.ntiles * 2 * d * sizeof(float)));
-    SKB_CUDA_C(cudaMalloc(&k->sboxes, (size_t)(hk.nsuper + hk.nchunk) * 2 * d * sizeof(float)));   // super-boxes, then chunk boxes
     float* cboxes = k->sboxes + (size_t)hk.nsuper * 2 * d;
-    SKB_CUDA_C(cudaMalloc(&d_perm, (size_t)hk.ntiles * TN * sizeof(int)));
-    SKB_CUDA_C(cudaMalloc(&k->dk, sizeof(KdeDev)));
+    SKB_CUDA_C(cudaMallocAsync(reinterpret_cast<void**>(&d_perm), (size_t)hk.ntiles * TN * sizeof(int), st));
     hk.zt64 = k->zt64;
     hk.cumsum_w = k->cumsum;
     hk.tiles = k->tiles;
@@ -681,7 +698,7 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
     if (!is_device_ptr(train)) {
         const size_t esz = train_dtype == SKB_F32 ? 4 : 8;
         const size_t bytes = ((size_t)(N - 1) * ld_train + d) * esz;
-        SKB_CUDA_C(cudaMalloc(&d_train_tmp, bytes));
+        SKB_CUDA_C(cudaMallocAsync(&d_train_tmp, bytes, st));
         SKB_CUDA_C(cudaMemcpyAsync(d_train_tmp, train, bytes, cudaMemcpyHostToDevice, st));
         d_train = d_train_tmp;
     }
@@ -709,12 +726,7 @@ int skb_destroy(skb_handle h)
     if (!h) return SKB_OK;
     DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
-    if (h->tiles) cudaFree(h->tiles);
-    if (h->boxes) cudaFree(h->boxes);
-    if (h->sboxes) cudaFree(h->sboxes);
-    if (h->zt64) cudaFree(h->zt64);
-    if (h->cumsum) cudaFree(h->cumsum);
-    if (h->dk) cudaFree(h->dk);
+    if (h->slab) cudaFree(h->slab);
     cudaGetLastError();
     delete h;
     return SKB_OK;

@@ -181,8 +181,12 @@ def _run(infodicts, layout):
     columns, bandwidth = info0["columns"], info0["bandwidth"]
     table = pd.concat([info["sample"] for info in infodicts])
     conts, colsets = [], []
+    rng_states = []
     for name, key, colkey in layout:
         emu = info0[key]["container"]
+        # the reference re-fits inside forked workers, which leaves the CALLER's containers (and their RandomState)
+        # untouched (emulator.py:698-712); fitting in-process must not advance the caller's stream either
+        rng_states.append((emu, emu.rng.get_state()))
         emu.standardize_data()
         emu.construct_kde(bandwidth=bandwidth)
         conts.append(emu)
@@ -193,6 +197,8 @@ def _run(infodicts, layout):
         jacs = [c._jacobian_det for c in conts]
         for c in conts:
             c.drop_kde()
+        for emu, state in rng_states:
+            emu.rng.set_state(state)
     # per-chunk frames concatenated, like pd.concat(result) of the pool's outputs (index restarts per chunk)
     frames = []
     a = 0
