@@ -695,6 +695,11 @@ def main():
         return 0
     if args.cpu_seconds is None:
         args.cpu_seconds = 20.0
+    # stdout carries exactly ONE JSON line: anything a library prints there at C level (NCCL's version banner, its
+    # NCCL_DEBUG log when no NCCL_DEBUG_FILE is honoured) is sent to stderr instead; NCCL_DEBUG itself is left alone
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     cpu = None
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -703,7 +708,7 @@ def main():
     if rank == 0:
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=real_stdout, flush=True)
     return 0
 
 

@@ -195,6 +195,30 @@ int skb_compact(const uint8_t* flags, int64_t M, const void* rows, int dtype, in
                 void* out, int64_t* out_index, int64_t* n_out, void* stream);
 
 /*
+ * Feature construction in front of the KDE fit (BaseContainer.construct_features, emulator.py:74-132): every feature is
+ * a catalogue column, a literal, or a binary expression of two of them; rows are kept when every feature lies inside its
+ * OPEN interval (lo, hi); features flagged log10 are replaced by their decimal logarithm.  One kernel, one thread per
+ * catalogue row; operands are DEVICE columns (element stride in elements, so a component of a vector column is just an
+ * offset pointer with the vector length as stride).  Arithmetic follows numpy: float32 when every array operand is
+ * float32 (literals are weak scalars), else float64; the stored feature is float64.
+ *   op: 0 = a, 1 = a - b, 2 = a + b, 3 = a * b, 4 = a / b, 5 = sqrt(a^2 + b^2)
+ *   out  [n_rows][n_feat] fp64 (all rows; rows with keep == 0 are to be dropped, e.g. with skb_compact), keep [n_rows].
+ */
+typedef struct skb_feature_spec {
+    const void* a;            /* device column or NULL (-> a_const) */
+    const void* b;            /* device column or NULL (-> b_const; ignored for op 0) */
+    int64_t     a_stride, b_stride;
+    double      a_const, b_const;
+    double      lo, hi;       /* open interval; -inf / +inf disable a side */
+    int32_t     a_dtype, b_dtype;   /* SKB_F64 / SKB_F32 */
+    int32_t     op;
+    int32_t     log10;
+} skb_feature_spec;
+
+int skb_features(const skb_feature_spec* specs /* HOST */, int n_feat, int64_t n_rows,
+                 double* out, uint8_t* keep, void* stream);
+
+/*
  * FP32-FMA / MUFU.EX2 pipe peaks measured live on the device (roofline denominators, H8 of
  * SURVEY.md): lane-FMAs per second through FFMA2, EX2 per second, over ~ms_each ms each.
  */

@@ -33,6 +33,17 @@ class SkbJob(C.Structure):
     ]
 
 
+class SkbFeatureSpec(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("b", C.c_void_p),
+        ("a_stride", C.c_int64), ("b_stride", C.c_int64),
+        ("a_const", C.c_double), ("b_const", C.c_double),
+        ("lo", C.c_double), ("hi", C.c_double),
+        ("a_dtype", C.c_int32), ("b_dtype", C.c_int32),
+        ("op", C.c_int32), ("log10", C.c_int32),
+    ]
+
+
 # name -> (restype, argtypes); the single source of truth the symbol-export test walks too
 SIGNATURES = {
     "skb_last_error": (C.c_char_p, []),
@@ -65,6 +76,7 @@ SIGNATURES = {
                            C.POINTER(C.c_int64), C.c_void_p]),
     "skb_compact": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
                               C.POINTER(C.c_int64), C.c_void_p]),
+    "skb_features": (C.c_int, [C.POINTER(SkbFeatureSpec), C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "skb_measure_pipes": (C.c_int, [C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "skb_debug_counters": (C.c_int, [C.c_int, C.POINTER(C.c_uint64), C.c_int]),
     "skb_launch_count": (C.c_int64, []),

@@ -1143,6 +1143,25 @@ int skb_compact(const uint8_t* flags, int64_t M, const void* rows, int dtype, in
     return SKB_OK;
 }
 
+int skb_features(const skb_feature_spec* specs, int n_feat, int64_t n_rows, double* out, uint8_t* keep, void* stream)
+{
+    if (!specs || n_feat < 1 || n_feat > SKB_MAXD) return fail(SKB_EINVAL, "feature count must be 1..%d", SKB_MAXD);
+    if (n_rows < 0) return fail(SKB_EINVAL, "negative row count");
+    if (n_rows == 0) return SKB_OK;
+    if (skb_device_count() <= 0) return fail(SKB_ECUDA, "no CUDA device available (this backend has no CPU fallback)");
+    if (!out || !keep || !is_device_ptr(out) || !is_device_ptr(keep)) return fail(SKB_EINVAL, "skb_features works on device buffers only");
+    for (int f = 0; f < n_feat; f++) {
+        const skb_feature_spec& s = specs[f];
+        if (s.op < 0 || s.op > 5) return fail(SKB_EINVAL, "feature %d: only + - * / and SQSUM are supported", f);
+        if (s.a && (!is_device_ptr(s.a) || (s.a_dtype != SKB_F64 && s.a_dtype != SKB_F32) || s.a_stride < 1))
+            return fail(SKB_EINVAL, "feature %d: operand a must be a float32 / float64 device column", f);
+        if (s.op != 0 && s.b && (!is_device_ptr(s.b) || (s.b_dtype != SKB_F64 && s.b_dtype != SKB_F32) || s.b_stride < 1))
+            return fail(SKB_EINVAL, "feature %d: operand b must be a float32 / float64 device column", f);
+    }
+    SKB_CUDA(launch_features(specs, n_feat, n_rows, out, keep, reinterpret_cast<cudaStream_t>(stream)));
+    return SKB_OK;
+}
+
 int skb_set_option(const char* name, int value)
 {
     if (!name) return fail(SKB_EINVAL, "NULL option name");

@@ -15,6 +15,7 @@
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
 #include <vector>
+#include <cstring>
 
 namespace skb {
 
@@ -351,6 +352,74 @@ cudaError_t launch_kd_order(const double* zt64, const double* w, long long N, lo
     kd_finish_kernel<<<(unsigned)((npad + bs - 1) / bs), bs, 0, st>>>(idx_cur, nv, npad, perm, root, D, kde_dev);
     count_launch();
     return done(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------
+// Feature construction (BaseContainer.construct_features, emulator.py:74-132) — elementwise, HBM bound
+// ---------------------------------------------------------------------------------------------
+struct FeatureProgram {
+    skb_feature_spec spec[SKB_MAXD];
+    int n;
+};
+
+template <class T>
+__device__ __forceinline__ T feature_op(int op, T a, T b)
+{
+    switch (op) {
+        case 1: return a - b;
+        case 2: return a + b;
+        case 3: return a * b;
+        case 4: return a / b;
+        default: return a;
+    }
+}
+// np.sqrt(a**2. + b**2.): two roundings for the squares and one for the sum — no FMA contraction
+__device__ __forceinline__ float feature_sqsum(float a, float b) { return sqrtf(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b))); }
+__device__ __forceinline__ double feature_sqsum(double a, double b) { return sqrt(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b))); }
+
+__global__ void __launch_bounds__(256)
+skb_features_kernel(const __grid_constant__ FeatureProgram P, long long n_rows, double* __restrict__ out,
+                    unsigned char* __restrict__ keep)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    bool ok = true;
+    for (int f = 0; f < P.n; f++) {
+        const skb_feature_spec& s = P.spec[f];
+        const bool a_arr = s.a != nullptr, b_arr = s.b != nullptr && s.op != 0;
+        // numpy promotion: float32 arithmetic only when every ARRAY operand is float32 (python literals are weak)
+        const bool f32 = (!a_arr || s.a_dtype == SKB_F32) && (!b_arr || s.b_dtype == SKB_F32) && (a_arr || b_arr);
+        double v;
+        if (f32) {
+            const float a = a_arr ? reinterpret_cast<const float*>(s.a)[r * s.a_stride] : (float)s.a_const;
+            const float b = b_arr ? reinterpret_cast<const float*>(s.b)[r * s.b_stride] : (float)s.b_const;
+            v = (double)(s.op == 5 ? feature_sqsum(a, b) : feature_op<float>(s.op, a, b));
+        } else {
+            const double a = !a_arr ? s.a_const
+                                    : (s.a_dtype == SKB_F32 ? (double)reinterpret_cast<const float*>(s.a)[r * s.a_stride]
+                                                            : reinterpret_cast<const double*>(s.a)[r * s.a_stride]);
+            const double b = !b_arr ? s.b_const
+                                    : (s.b_dtype == SKB_F32 ? (double)reinterpret_cast<const float*>(s.b)[r * s.b_stride]
+                                                            : reinterpret_cast<const double*>(s.b)[r * s.b_stride]);
+            v = s.op == 5 ? feature_sqsum(a, b) : feature_op<double>(s.op, a, b);
+        }
+        ok = ok && (v > s.lo) && (v < s.hi);                // open interval; NaN fails both, as in the reference
+        out[r * P.n + f] = s.log10 ? log10(v) : v;
+    }
+    keep[r] = ok ? 1 : 0;
+}
+
+cudaError_t launch_features(const skb_feature_spec* specs, int n_feat, long long n_rows, double* out, unsigned char* keep,
+                            cudaStream_t st)
+{
+    if (n_rows <= 0) return cudaSuccess;
+    FeatureProgram P;
+    memset(&P, 0, sizeof(P));
+    P.n = n_feat;
+    for (int f = 0; f < n_feat; f++) P.spec[f] = specs[f];
+    skb_features_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(P, n_rows, out, keep);
+    count_launch();
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -209,6 +209,8 @@ cudaError_t launch_query_order(const KdeDev* kde, const void* q, int q_f32, long
                                cudaStream_t st);
 cudaError_t launch_kd_order(const double* zt64, const double* w, long long N, long long nv, int D, double c,
                             int* perm, KdeDev* kde_dev, cudaStream_t st);
+cudaError_t launch_features(const skb_feature_spec* specs, int n_feat, long long n_rows, double* out, unsigned char* keep,
+                            cudaStream_t st);
 size_t sparse_scan_temp_bytes();
 cudaError_t sparse_prepare();
 cudaError_t launch_sparse_group(int D, const ScoreLaunch& L, int nl, const SparseLaunch& SLh, const SparseLaunch* SLd,

@@ -2,9 +2,12 @@
 
 ``BaseContainer.construct_features`` (column algebra, limits, log10), ``DeepFeatureContainer``,
 ``FeatureSpaceContainer`` (radially balanced, weight-preserving downsample) and the two
-``construct_*_container`` helpers the drivers call before ``make_*_infodicts``.  This is O(N) pandas
-bookkeeping done once per run; it stays on the host and hands a ``KDEContainer`` of this package to the
-GPU path.  Same names, arguments and results as the reference; differences are noted inline.
+``construct_*_container`` helpers the drivers call before ``make_*_infodicts``.  Same names, arguments and
+results as the reference; differences are noted inline.  ``construct_features(..., device=k)`` runs the column
+algebra, the limit cuts and the log10 on GPU k (``skb_features`` + ``skb_compact``: one elementwise kernel over the
+catalogue rows and an order-preserving compaction) and brings the same DataFrame back; ``features_on_device`` keeps the
+result there (torch CUDA tensors ready for ``GaussianKDE.fit``).  The radially balanced downsample stays on the host:
+its draws are defined by numpy's ``RandomState.choice(replace=False, p=...)`` stream.
 """
 import copy
 
@@ -37,11 +40,85 @@ class BaseContainer(object):
             return self.alldata[spec[0]][:, spec[1]]
         return spec
 
-    def construct_features(self, columns, limits=None, logs=None, **kwargs):
-        """emulator.py:74-132: build the feature columns, cut on ``limits`` (open intervals), then log10."""
+    _OPCODES = {"-": 1, "+": 2, "*": 3, "/": 4, "SQSUM": 5}
+
+    def features_on_device(self, columns, limits=None, logs=None, device=0):
+        """The feature table on GPU ``device``: (features [n_keep, d] float64 CUDA tensor, kept row ids int64 CUDA tensor).
+        Same column algebra / cuts / log10 as ``construct_features`` (emulator.py:74-132), evaluated by ``skb_features``."""
+        import ctypes as C
+        import torch
+        from . import _cabi
+        dev = torch.device("cuda", device)
+        n = len(self.alldata)
+        cache, keepalive = {}, []
+
+        def operand(spec):
+            """-> (device pointer or None, dtype code, stride, constant)"""
+            if isinstance(spec, str) or isinstance(spec, (list, tuple)):
+                name, comp = (spec, None) if isinstance(spec, str) else (spec[0], spec[1])
+                if name not in cache:
+                    arr = np.asarray(self.alldata[name])
+                    if arr.dtype not in (np.float32, np.float64):
+                        arr = arr.astype(np.float64)
+                    cache[name] = torch.from_numpy(np.ascontiguousarray(arr)).to(dev)
+                t = cache[name]
+                stride = 1 if t.dim() == 1 else t.shape[1]
+                off = 0 if comp is None else int(comp)
+                return t.data_ptr() + off * t.element_size(), _cabi.dtype_code(t), stride, 0.0
+            return None, _cabi.SKB_F64, 1, float(spec)
+
+        specs = (_cabi.SkbFeatureSpec * len(columns))()
+        for i, (name, src) in enumerate(columns):
+            sp = specs[i]
+            if isinstance(src, str):
+                a, b, op = src, 0.0, 0
+            elif len(src) == 3:
+                if src[2] not in self._OPCODES:
+                    raise KeyError("only + - * / are supported at the moment")
+                a, b, op = src[0], src[1], self._OPCODES[src[2]]
+            elif len(src) == 2:
+                a, b, op = (src[0], src[1]), 0.0, 0
+            else:
+                raise KeyError
+            pa, da, sa, ca = operand(a)
+            pb, db, sb, cb = operand(b)
+            sp.a, sp.a_dtype, sp.a_stride, sp.a_const = pa, da, sa, ca
+            sp.b, sp.b_dtype, sp.b_stride, sp.b_const = pb, db, sb, cb
+            sp.op = op
+            sp.lo = float(limits[i][0]) if limits is not None else -np.inf
+            sp.hi = float(limits[i][1]) if limits is not None else np.inf
+            sp.log10 = 1 if (logs is not None and logs[i]) else 0
+        d = len(columns)
+        out = torch.empty((n, d), dtype=torch.float64, device=dev)
+        keep = torch.empty(n, dtype=torch.uint8, device=dev)
+        st = torch.cuda.current_stream(dev)
+        lib = _cabi.lib()
+        _cabi.check(lib.skb_features(specs, d, n, _cabi.ptr(out), _cabi.ptr(keep), _cabi.stream_ptr(st)))
+        packed = torch.empty_like(out)
+        index = torch.empty(n, dtype=torch.int64, device=dev)
+        cnt = C.c_int64(0)
+        _cabi.check(lib.skb_compact(_cabi.ptr(keep), n, _cabi.ptr(out), _cabi.SKB_F64, d, _cabi.ptr(packed), _cabi.ptr(index),
+                                    C.byref(cnt), _cabi.stream_ptr(st)))
+        k = int(cnt.value)
+        return packed[:k], index[:k]
+
+    def construct_features(self, columns, limits=None, logs=None, device=None, **kwargs):
+        """emulator.py:74-132: build the feature columns, cut on ``limits`` (open intervals), then log10.
+        ``device=k``: the same table computed on GPU k (see ``features_on_device``) and copied back."""
         self.columns = columns
         self.limits = limits
         self.logs = logs
+        if device is not None:
+            feats, index = self.features_on_device(columns, limits=limits, logs=logs, device=device)
+            rows = index.cpu().numpy()
+            self.inds = np.zeros(len(self.alldata), dtype=bool)
+            self.inds[rows] = True
+            self.features = pd.DataFrame(feats.cpu().numpy(), columns=[c[0] for c in columns], index=rows)
+            try:
+                self.weights = self.alldata["WEIGHT"][self.inds]
+            except Exception:
+                self.weights = pd.Series(data=np.ones(len(self.features)), name="WEIGHT")
+            return
         self.features = pd.DataFrame()
         self.inds = np.ones(len(self.alldata), dtype=bool)
         for i, (name, src) in enumerate(columns):

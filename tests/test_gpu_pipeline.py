@@ -286,3 +286,50 @@ def test_fused_ratio_accept_mixes_both_score_kernels():
     for c in conts:
         c.drop_kde()
     assert not mismatch, "(dimension, rows that differ, max |d log p|) per member: %r" % (mismatch,)
+
+
+def test_feature_construction_on_the_device_matches_the_reference_tables():
+    """construct_features(device=0): column algebra, limit cuts and log10 in ONE kernel + the order-preserving compaction,
+    against the reference's own feature tables (tests/golden/features.npz, emulator.py:74-132) and against the host
+    mirror for float32 catalogues (numpy's promotion rules: float32 arithmetic, float64 storage)."""
+    from conftest import load_golden
+    from skysampler_b200 import features
+    g = load_golden("features")
+    nd = len(g["deep_MAG_G"])
+    deep = np.zeros(nd, dtype=[("MAG_G", "f8"), ("MAG_R", "f8"), ("MAG_I", "f8"), ("MAG_Z", "f8"), ("SIZE", "f8"), ("E", "f8", (2,))])
+    for n in ("MAG_G", "MAG_R", "MAG_I", "MAG_Z", "SIZE", "E"):
+        deep[n] = g["deep_" + n]
+    settings = {
+        "columns": [("MAG_I", "MAG_I"), ("COLOR_G_R", ("MAG_G", "MAG_R", "-")), ("COLOR_R_I", ("MAG_R", "MAG_I", "-")),
+                    ("LOGSIZE", "SIZE"), ("ELL", (("E", 0), ("E", 1), "SQSUM")), ("E1", ("E", 1))],
+        "logs": [False, False, False, True, False, False],
+        "limits": [(19, 24), (-1, 3), (-1, 3), (1e-3, 2.0), (0, 10), (-5, 5)],
+    }
+    dfc = features.DeepFeatureContainer(deep)
+    dfc.construct_features(device=0, **settings)
+    np.testing.assert_array_equal(np.asarray(dfc.features.index), g["deep_feature_index"])
+    got, ref = dfc.features.values, g["deep_features"]
+    logcol = 3
+    for c in range(got.shape[1]):
+        if c == logcol:
+            np.testing.assert_allclose(got[:, c], ref[:, c], rtol=4e-16, atol=0)       # log10: within 2 ulp of numpy's
+        else:
+            np.testing.assert_array_equal(got[:, c], ref[:, c])
+    np.testing.assert_array_equal(np.asarray(dfc.weights), g["deep_weights"])
+    # float32 catalogue + literals + every operator: device == host mirror
+    rs = np.random.RandomState(4)
+    cat = np.zeros(20000, dtype=[("A", "f4"), ("B", "f4"), ("V", "f4", (3,)), ("W8", "f8")])
+    cat["A"] = rs.uniform(0.5, 3, 20000); cat["B"] = rs.uniform(0.5, 3, 20000); cat["V"] = rs.normal(size=(20000, 3)); cat["W8"] = rs.uniform(1, 2, 20000)
+    cols = [("S", ("A", "B", "+")), ("D", ("A", "B", "-")), ("P", ("A", "W8", "*")), ("Q", ("A", "B", "/")),
+            ("R", (("V", 0), ("V", 2), "SQSUM")), ("K", ("A", 2.5, "*")), ("V1", ("V", 1)), ("LA", "A")]
+    lims = [(1.2, 5.5), (-2, 2), (0.6, 5.5), (0.2, 5), (0.05, 3), (1.3, 7.4), (-2.5, 2.5), (0.5, 3)]
+    logs = [False, False, True, False, True, False, False, True]
+    host = features.DeepFeatureContainer(cat); host.construct_features(cols, limits=lims, logs=logs)
+    devc = features.DeepFeatureContainer(cat); devc.construct_features(cols, limits=lims, logs=logs, device=0)
+    np.testing.assert_array_equal(np.asarray(devc.features.index), np.asarray(host.features.index))
+    assert 2000 < len(host.features) < 19000
+    for c, lg in enumerate(logs):
+        np.testing.assert_allclose(devc.features.values[:, c], host.features.values[:, c], rtol=4e-16 if lg else 0, atol=0)
+    # and it can stay on the device for the fit
+    feats, index = devc.features_on_device(cols, limits=lims, logs=logs, device=0)
+    assert feats.is_cuda and feats.shape == (len(host.features), 8) and index.shape[0] == len(host.features)
