@@ -82,13 +82,19 @@ constexpr int PQ_ROW = 32;                        // part[query][lane ^ query]: 
 #ifndef SKB_PQ_SLACK
 #define SKB_PQ_SLACK 3        // a lane term >= 2^(SLACK - REF_BIAS) (a point that much closer than the reference) recentres
 #endif
+#ifndef SKB_PQ_LDG
+#define SKB_PQ_LDG 1          // 1: a lane reads its two points of a tile straight from L2 (coalesced LDG.64 rows), no smem ring
+#endif
+#ifndef SKB_PQ_PREFETCH
+#define SKB_PQ_PREFETCH 0     // (LDG mode) 1: the next work-list entry's points are loaded before this entry's pair loop
+#endif
 static_assert(PQ_CH <= 32 && PQ_CAP <= 256 && SG == 16, "PQ chunk layout");
 __host__ __device__ constexpr bool pq_mode(int D, int Q) { return SKB_PQ && D >= SKB_PQ_MIN_D && Q == 1 && tile_points(D) == 64; }
 __host__ __device__ constexpr int pq_qstride(int D) { return (D + 4) & ~3; }          // floats per query row: z[0..D), -m, padding to 16 B
 __host__ __device__ constexpr size_t pq_smem_bytes(int D)
 {
-    return (size_t)SKB_NSTAGE_PQ * stage_floats(D) * 4 + (size_t)SKB_NSTAGE_PQ * 16 + (size_t)32 * pq_qstride(D) * 4 +
-           (size_t)32 * PQ_ROW * 4 + (size_t)PQ_CAP * 4 + (size_t)PQ_CAP + 16;
+    return (SKB_PQ_LDG ? (size_t)0 : (size_t)SKB_NSTAGE_PQ * stage_floats(D) * 4 + (size_t)SKB_NSTAGE_PQ * 16) +
+           (size_t)32 * pq_qstride(D) * 4 + (size_t)32 * PQ_ROW * 4 + (size_t)PQ_CAP * 4 + (size_t)PQ_CAP + 16;
 }
 
 // acc - m for this lane's two points against the query row in shared memory.  The row holds plain floats:
@@ -413,11 +419,12 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
     finish_queries<D, Q>(L, job, qbase, tid, M, mref, S, s_last);
 }
 
-template <int D>
+template <int D, bool STATS>
 __global__ void __launch_bounds__(32, D <= 8 ? SKB_PQ_MINB : (D <= 12 ? SKB_PQ_MINB_HI : 16))
 skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
 {
     constexpr int Q = 1;
+    constexpr bool LDG = SKB_PQ_LDG != 0;
     constexpr int TN = tile_points(D);
     constexpr int QS = pq_qstride(D);
     constexpr int STAGE_FLOATS = stage_floats(D);
@@ -433,9 +440,9 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stages = reinterpret_cast<float*>(smem_raw);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NSTAGE * STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + NSTAGE;
-    float* rows = reinterpret_cast<float*>(empty_bar + NSTAGE);       // 32 query rows: z[0..D), -m
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (LDG ? (size_t)0 : (size_t)NSTAGE * STAGE_BYTES));
+    uint64_t* empty_bar = full_bar + (LDG ? 0 : NSTAGE);
+    float* rows = reinterpret_cast<float*>(empty_bar + (LDG ? 0 : NSTAGE));       // 32 query rows: z[0..D), -m
     float* part = rows + 32 * QS;                                     // part[query][lane ^ query]
     unsigned* lmask = reinterpret_cast<unsigned*>(part + 32 * PQ_ROW);   // work list: query mask ...
     unsigned char* ltile = reinterpret_cast<unsigned char*>(lmask + PQ_CAP);   // ... and tile offset in the chunk
@@ -448,7 +455,7 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
     const int t0 = (int)(((long long)ntiles * blockIdx.z) / nsplit);
     const int t1 = (int)(((long long)ntiles * (blockIdx.z + 1)) / nsplit);
 
-    if (lane == 0) {
+    if (!LDG && lane == 0) {
 #pragma unroll
         for (int s = 0; s < NSTAGE; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_fence_init();
@@ -586,21 +593,33 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
         }
         __syncwarp();
         if (cnt == 0) continue;
-        n_visited += (unsigned)cnt;
+        if constexpr (STATS) n_visited += (unsigned)cnt;
 
-        // ---- (3) stream the work list through the ring ----
+        // ---- (3) stream the work list.  LDG mode: every lane reads its two points of a tile straight from L2 (one coalesced
+        //          256-byte row per dimension), no shared-memory ring and no barriers; ring mode: 1-D TMA copies ----
         const int tchunk = s_base * SG;
-        if (lane == 0) {
+        if (!LDG && lane == 0) {
             const int npre = cnt < NSTAGE ? cnt : NSTAGE;
             for (int e = 0; e < npre; e++) request(it + (unsigned)e, tchunk + ltile[e]);
         }
+        u64 p2[D];
+        float w0, w1;
+        auto fetch = [&](int t, u64 (&pp)[D], float& ww0, float& ww1) {
+            const float* __restrict__ tile = gtiles + (size_t)t * STAGE_FLOATS + 2 * lane;
+#pragma unroll
+            for (int k = 0; k < D; k++) pp[k] = __ldg(reinterpret_cast<const u64*>(tile + k * TN));
+            upk(__ldg(reinterpret_cast<const u64*>(tile + D * TN)), ww0, ww1);
+        };
+#if SKB_PQ_LDG && SKB_PQ_PREFETCH
+        u64 pn[D];
+        float wn0, wn1;
+        fetch(tchunk + ltile[0], pn, wn0, wn1);
+#endif
 #pragma unroll 1
         for (int e = 0; e < cnt; e++, it++) {
             const int s = (int)(it % NSTAGE);
             unsigned mask = lmask[e];
             const int tcur = tchunk + ltile[e];
-            mbar_wait(&full_bar[s], (it / NSTAGE) & 1u);
-            const float* tile = stages + (size_t)s * STAGE_FLOATS;
 
             const int epoch = tcur >> PQ_EPOCH_SHIFT;
             if (epoch != epoch_cur) {
@@ -608,18 +627,29 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
                 epoch_cur = epoch;
             }
             // this lane's two points of the tile
-            u64 p2[D];
+            if constexpr (LDG) {
+#if SKB_PQ_LDG && SKB_PQ_PREFETCH
 #pragma unroll
-            for (int k = 0; k < D; k++) p2[k] = *reinterpret_cast<const u64*>(tile + k * TN + 2 * lane);
-            float w0, w1;
-            upk(*reinterpret_cast<const u64*>(tile + D * TN + 2 * lane), w0, w1);
-            n_pairs += 2u * __popc(mask);
-            // the tile now lives in registers: hand the stage back and request the tile NSTAGE entries ahead
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&empty_bar[s]);
-                if (e + NSTAGE < cnt) request(it + (unsigned)NSTAGE, tchunk + ltile[e + NSTAGE]);
+                for (int k = 0; k < D; k++) p2[k] = pn[k];
+                w0 = wn0; w1 = wn1;
+                if (e + 1 < cnt) fetch(tchunk + ltile[e + 1], pn, wn0, wn1);
+#else
+                fetch(tcur, p2, w0, w1);
+#endif
+            } else {
+                mbar_wait(&full_bar[s], (it / NSTAGE) & 1u);
+                const float* tile = stages + (size_t)s * STAGE_FLOATS;
+#pragma unroll
+                for (int k = 0; k < D; k++) p2[k] = *reinterpret_cast<const u64*>(tile + k * TN + 2 * lane);
+                upk(*reinterpret_cast<const u64*>(tile + D * TN + 2 * lane), w0, w1);
+                // the tile now lives in registers: hand the stage back and request the tile NSTAGE entries ahead
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&empty_bar[s]);
+                    if (e + NSTAGE < cnt) request(it + (unsigned)NSTAGE, tchunk + ltile[e + NSTAGE]);
+                }
             }
+            if constexpr (STATS) n_pairs += 2u * __popc(mask);
 
             // rare: a point >= 8 binades closer than the reference was built for (or a NaN row) — fold the
             // row, move the query's reference to the tile's closest point, re-evaluate
@@ -628,7 +658,7 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
 #pragma unroll
                 for (int off = 16; off >= 1; off >>= 1) am = fminf(am, __shfl_xor_sync(FULL, am, off));
                 const float delta = floorf(am) - ref_bias;
-                n_rerun++;
+                if constexpr (STATS) n_rerun++;
                 if (delta < 0.f && delta > -1.0e30f) {
                     __syncwarp();
                     if (lane == i) {
@@ -684,7 +714,7 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
     __syncwarp();
     S[0] += pq_fold_row(part, lane);
 
-    if (job.stats && lane == 0) {
+    if (STATS && job.stats && lane == 0) {
         if (n_rerun) atomicAdd(&job.stats[0], (unsigned long long)n_rerun * 2);
         atomicAdd(&job.stats[1], n_pairs);
         atomicAdd(&job.stats[2], (unsigned long long)((unsigned)(t1 - t0) - n_visited));
@@ -701,9 +731,12 @@ static cudaError_t launch_score_dq(const ScoreLaunch& L, int njobs, long long ma
     dim3 grid((unsigned)((max_rows + QB - 1) / QB), (unsigned)njobs, (unsigned)max_split);
     if constexpr (pq_mode(D, Q)) {
         const size_t smem = pq_smem_bytes(D);
-        cudaError_t e = cudaFuncSetAttribute(skb_score_pq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        bool stats = false;
+        for (int j = 0; j < njobs; j++) stats |= (L.jobs[j].stats != nullptr);
+        auto kern = stats ? skb_score_pq_kernel<D, true> : skb_score_pq_kernel<D, false>;   // counters are compiled out of the release kernel
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        skb_score_pq_kernel<D><<<grid, 32, smem, st>>>(L);
+        kern<<<grid, 32, smem, st>>>(L);
     } else {
         constexpr int NSTAGE = nstage(D);
         const size_t smem = (size_t)NSTAGE * stage_floats(D) * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t) +
@@ -723,8 +756,8 @@ static int occupancy_dq()
     cudaError_t e;
     if constexpr (pq_mode(D, Q)) {
         const size_t smem = pq_smem_bytes(D);
-        e = cudaFuncSetAttribute(skb_score_pq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, skb_score_pq_kernel<D>, 32, smem);
+        e = cudaFuncSetAttribute(skb_score_pq_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, skb_score_pq_kernel<D, false>, 32, smem);
     } else {
         constexpr int NSTAGE = nstage(D);
         const size_t smem = (size_t)NSTAGE * stage_floats(D) * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t) + 1024;
