@@ -72,7 +72,7 @@ namespace skb {
 constexpr int PQ_CH = CG;                         // one work list per chunk box
 constexpr int PQ_CAP = PQ_CH * SG;                // work-list capacity: every tile of a chunk
 constexpr int PQ_EPOCH_SHIFT = SKB_PQ_EPOCH_SHIFT;                 // fp32 row partials are folded into fp64 every 256 tile indices
-constexpr int PQ_ROW = 32;                        // part[query][lane ^ query]: conflict-free for both walks
+constexpr int PQ_ROW = 33;                        // part[query][lane], rows padded by one word: conflict-free for both walks
 #ifndef SKB_PQ_UNROLL
 #define SKB_PQ_UNROLL 2       // queries of a tile's mask evaluated per step (2 or 4)
 #endif
@@ -126,8 +126,8 @@ __device__ __forceinline__ double pq_fold_row(float* __restrict__ part, int row)
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
     for (int l = 0; l < 32; l += 4) {
-        s0 += (double)p[l ^ row]; s1 += (double)p[(l + 1) ^ row]; s2 += (double)p[(l + 2) ^ row]; s3 += (double)p[(l + 3) ^ row];
-        p[l ^ row] = 0.f; p[(l + 1) ^ row] = 0.f; p[(l + 2) ^ row] = 0.f; p[(l + 3) ^ row] = 0.f;
+        s0 += (double)p[l]; s1 += (double)p[l + 1]; s2 += (double)p[l + 2]; s3 += (double)p[l + 3];
+        p[l] = 0.f; p[l + 1] = 0.f; p[l + 2] = 0.f; p[l + 3] = 0.f;
     }
     return __dadd_rn(__dadd_rn(s0, s1), __dadd_rn(s2, s3));
 }
@@ -443,7 +443,7 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (LDG ? (size_t)0 : (size_t)NSTAGE * STAGE_BYTES));
     uint64_t* empty_bar = full_bar + (LDG ? 0 : NSTAGE);
     float* rows = reinterpret_cast<float*>(empty_bar + (LDG ? 0 : NSTAGE));       // 32 query rows: z[0..D), -m
-    float* part = rows + 32 * QS;                                     // part[query][lane ^ query]
+    float* part = rows + 32 * QS;                                     // part[query][lane], rows of PQ_ROW words
     unsigned* lmask = reinterpret_cast<unsigned*>(part + 32 * PQ_ROW);   // work list: query mask ...
     unsigned char* ltile = reinterpret_cast<unsigned char*>(lmask + PQ_CAP);   // ... and tile offset in the chunk
     __shared__ int s_last[32 / FB];
@@ -475,7 +475,8 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
 #pragma unroll
     for (int k = 0; k < D; k++) rows[lane * QS + k] = q2[0][k];
     rows[lane * QS + D] = -mref[0];
-    for (int l = 0; l < 32; l++) part[lane * PQ_ROW + l] = 0.f;
+    for (int l = 0; l < 32; l++) part[l * PQ_ROW + lane] = 0.f;
+    float* const mypart = part + lane;                                 // + query * PQ_ROW
     __syncwarp();
 
     const float* __restrict__ cbx = kde->cboxes;
@@ -684,7 +685,7 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
 #pragma unroll
                 for (int n = 0; n < NQ; n++) { idx[n] = 31 - __clz(mask); mask ^= 1u << idx[n]; }   // highest set bit: one FLO, no BREV
 #pragma unroll
-                for (int n = 0; n < NQ; n++) pa[n] = part[idx[n] * PQ_ROW + (lane ^ idx[n])];   // issued early: off the critical path
+                for (int n = 0; n < NQ; n++) pa[n] = mypart[idx[n] * PQ_ROW];   // issued early: off the critical path
 #pragma unroll
                 for (int n = 0; n < NQ; n++) pq_acc<D>(rows + idx[n] * QS, p2, a0[n], a1[n]);
                 bool bad = false;
@@ -698,11 +699,11 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
                     for (int n = 0; n < NQ; n++)
                         if (__any_sync(FULL, !(t[n] < PQ_LIMIT))) {
                             t[n] = recentre(idx[n], a0[n], a1[n]);
-                            pa[n] = part[idx[n] * PQ_ROW + (lane ^ idx[n])];
+                            pa[n] = mypart[idx[n] * PQ_ROW];
                         }
                 }
 #pragma unroll
-                for (int n = 0; n < NQ; n++) part[idx[n] * PQ_ROW + (lane ^ idx[n])] = pa[n] + t[n];
+                for (int n = 0; n < NQ; n++) mypart[idx[n] * PQ_ROW] = pa[n] + t[n];
             };
             if constexpr (SKB_PQ_UNROLL >= 4 || D <= SKB_PQ_UNROLL4_MAX_D)
                 while (__popc(mask) >= 4) eval(std::integral_constant<int, 4>{});

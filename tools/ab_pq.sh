@@ -1,5 +1,5 @@
 set -x
-for v in ring default ldg24 pf20 pf22; do
+for v in ${VARIANTS:-ring default}; do
   if [ $v = default ]; then unset SKB_LIB_PATH; else export SKB_LIB_PATH=$PWD/tools/variants/$v/libskb.so; fi
   python tools/ab_pq.py 8,12,16 1000000 $v 2>&1 | grep -v Warning
 done > gpurun_out/ab_pq.txt 2>&1
