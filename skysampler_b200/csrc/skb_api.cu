@@ -666,6 +666,8 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
         auto carve = [&off](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
         const size_t o_zt = carve((size_t)N * d * sizeof(double));
         const size_t o_cs = carve(w ? (size_t)N * sizeof(double) : 0);
+        hk.cs_buckets = w ? (int)(N < (1ll << 24) ? N : (1ll << 24)) : 0;
+        const size_t o_ci = carve(w ? ((size_t)hk.cs_buckets + 1) * sizeof(int) : 0);
         const size_t o_tiles = carve(tile_bytes);
         const size_t o_boxes = carve((size_t)hk.ntiles * 2 * d * sizeof(float));
         const size_t o_sb = carve((size_t)(hk.nsuper + hk.nchunk) * 2 * d * sizeof(float));   // super-boxes, then chunk boxes
@@ -674,6 +676,7 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
         char* base = reinterpret_cast<char*>(k->slab);
         k->zt64 = reinterpret_cast<double*>(base + o_zt);
         k->cumsum = w ? reinterpret_cast<double*>(base + o_cs) : nullptr;
+        hk.cs_index = w ? reinterpret_cast<int*>(base + o_ci) : nullptr;
         k->tiles = reinterpret_cast<float*>(base + o_tiles);
         k->boxes = reinterpret_cast<float*>(base + o_boxes);
         k->sboxes = reinterpret_cast<float*>(base + o_sb);
@@ -681,6 +684,7 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
     }
     if (w) {
         SKB_CUDA_C(cudaMemcpyAsync(k->cumsum, cs.data(), (size_t)N * 8, cudaMemcpyHostToDevice, st));
+        SKB_CUDA_C(launch_cs_index(k->cumsum, N, const_cast<int*>(hk.cs_index), hk.cs_buckets, st));
         SKB_CUDA_C(cudaMallocAsync(reinterpret_cast<void**>(&d_w), (size_t)N * 8, st));
         SKB_CUDA_C(cudaMemcpyAsync(d_w, wh.data(), (size_t)N * 8, cudaMemcpyHostToDevice, st));
     }
@@ -1123,7 +1127,7 @@ int skb_compact(const uint8_t* flags, int64_t M, const void* rows, int dtype, in
     const void* ptrs[] = {flags, rows, out, out_index};
     for (const void* p : ptrs)
         if (p && !is_device_ptr(p)) return fail(SKB_EINVAL, "skb_compact works on device buffers only");
-    const long long nb = compact_nblocks(M);
+    const long long nb = compact_ws_words(M) - 1;                       // ticket + one state word per chunk, then the total
     unsigned long long* ws = nullptr;
     SKB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), (size_t)(nb + 1) * 8, st));
     cudaError_t e = launch_compact(flags, M, rows, dtype == SKB_F32 ? 4 : 8, ld, out,

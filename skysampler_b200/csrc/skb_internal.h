@@ -93,6 +93,8 @@ struct KdeDev {
     const float* tiles;      // [ntiles][D+2][tile_points(D)]
     const double* zt64;      // [N][D] whitened fp64 rows (draw centres)
     const double* cumsum_w;  // [N] sequential fp64 cumsum (NULL for unweighted)
+    const int* cs_index;     // [cs_buckets + 1] cs_index[b] = searchsorted(cumsum_w, b / cs_buckets * cumsum_w[N-1]): brackets the draw's search
+    int cs_buckets;
     const float* boxes;      // [ntiles][2][D] lo / hi of the packed fp32 coordinates
     const float* sboxes;     // [nsuper][2][D] union boxes of SG consecutive tiles
     const float* cboxes;     // [nchunk][2][D] union boxes of CG consecutive super-boxes
@@ -225,11 +227,13 @@ cudaError_t launch_draw(const KdeDev* kde, int D, long long M, const double* u, 
                         int rcol, double rmin, double rmax, int max_attempts,
                         long long* out_idx, double* out_x, long long ld_out, double* out_z,
                         unsigned char* out_flag, unsigned long long* n_flagged, cudaStream_t st);
+cudaError_t launch_cs_index(const double* cumsum, long long N, int* index, int buckets, cudaStream_t st);
 cudaError_t launch_compact(const unsigned char* flags, long long M, const void* rows, int elem_bytes,
                            long long ld, void* out, long long* out_index,
                            unsigned long long* block_counts, unsigned long long* total,
                            cudaStream_t st);
 long long compact_nblocks(long long M);
+long long compact_ws_words(long long M);
 cudaError_t measure_pipes(double ms_each, double* fma_lane_per_s, double* ex2_per_s);
 
 void count_launch(int n = 1);

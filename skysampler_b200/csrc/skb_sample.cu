@@ -42,6 +42,36 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, fl
     n0 = rad * c; n1 = rad * s;
 }
 
+// np.searchsorted(cs, target) (side='left') restricted to [lo, hi]; the caller guarantees the answer lies there.
+__device__ __forceinline__ long long lower_bound_f64(const double* __restrict__ cs, long long lo, long long hi, double target)
+{
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (__ldg(cs + mid) < target) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// Bucket index of the cumulative weights: index[b] = searchsorted(cs, b / B * cs[N-1]), b = 0..B.  A draw with uniform u
+// then only has to search cs[index[b-1] .. index[b+2]] with b = floor(u B) (about three entries when B = N) instead of
+// taking ~20 dependent probes of the whole array; the result is the same index bit for bit.
+__global__ void __launch_bounds__(256)
+cs_index_kernel(const double* __restrict__ cs, long long N, int* __restrict__ index, int B)
+{
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > B) return;
+    const double target = ((double)b / (double)B) * __ldg(cs + N - 1);
+    index[b] = (int)lower_bound_f64(cs, 0, N, target);
+}
+
+cudaError_t launch_cs_index(const double* cumsum, long long N, int* index, int buckets, cudaStream_t st)
+{
+    if (!cumsum || buckets <= 0) return cudaSuccess;
+    cs_index_kernel<<<(unsigned)(((long long)buckets + 1 + 255) / 256), 256, 0, st>>>(cumsum, N, index, buckets);
+    count_launch();
+    return cudaGetLastError();
+}
+
 // D is a template parameter: the per-draw vectors live in registers (with a run-time D they were local-memory arrays).
 template <int D>
 __global__ void __launch_bounds__(256)
@@ -57,6 +87,8 @@ skb_draw_kernel(const KdeDev* __restrict__ kde, long long M,
     if (i >= M) return;
     const long long N = kde->N;
     const double* __restrict__ cs = kde->cumsum_w;
+    const int* __restrict__ ci = kde->cs_index;
+    const long long nb = kde->cs_buckets;
     const double h = kde->h;
     const bool streams = (u_in != nullptr);
     const bool has_winv = kde->has_winv != 0;
@@ -79,19 +111,35 @@ skb_draw_kernel(const KdeDev* __restrict__ kde, long long M,
             // np.searchsorted(cumsum_weight, u * sum_weight)  (side='left')   sklearn _kde.py:345-347
             const double target = u * __ldg(cs + N - 1);
             long long lo = 0, hi = N;
-            while (lo < hi) {
-                const long long mid = (lo + hi) >> 1;
-                if (__ldg(cs + mid) < target) lo = mid + 1; else hi = mid;
+            if (ci && u >= 0.0 && u < 1.0) {
+                // u lies in [(b - 1) / B, (b + 2) / B) whatever way u * B rounded, and the fp64 product with cs[N-1] is
+                // monotone in u: the answer is bracketed by the index entries of those two bucket edges
+                long long b = (long long)(u * (double)nb);
+                b = b < 0 ? 0 : (b > nb - 1 ? nb - 1 : b);
+                lo = __ldg(ci + (b > 0 ? b - 1 : 0));
+                hi = __ldg(ci + (b + 2 < nb ? b + 2 : nb));
             }
+            lo = lower_bound_f64(cs, lo, hi, target);
             idx = lo < N ? lo : N - 1;
         } else {
             idx = (long long)(u * (double)N);              // (u * N).astype(int64)   sklearn _kde.py:343
             if (idx >= N) idx = N - 1;
         }
         const double* __restrict__ ctr = kde->zt64 + idx * D;
+        double cz[D];
+        if (D % 2 == 0) {                                  // rows of an even number of doubles are 16-byte aligned in the slab
+#pragma unroll
+            for (int k = 0; k < D; k += 2) {
+                const double2 v = __ldg(reinterpret_cast<const double2*>(ctr + k));
+                cz[k] = v.x; cz[k + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < D; k++) cz[k] = __ldg(ctr + k);
+        }
         if (streams) {
 #pragma unroll
-            for (int k = 0; k < D; k++) zs[k] = __dadd_rn(__ldg(ctr + k), __dmul_rn(h, z_in[i * D + k]));   // rng.normal(data[i], h): loc + scale*g, two roundings like numpy
+            for (int k = 0; k < D; k++) zs[k] = __dadd_rn(cz[k], __dmul_rn(h, z_in[i * D + k]));   // rng.normal(data[i], h): loc + scale*g, two roundings like numpy
         } else {
 #pragma unroll
             for (int k = 0; k < D; k += 4) {
@@ -102,7 +150,7 @@ skb_draw_kernel(const KdeDev* __restrict__ kde, long long M,
                 box_muller(r.z, r.w, n[2], n[3]);
 #pragma unroll
                 for (int t = 0; t < 4; t++)
-                    if (k + t < D) zs[k + t] = __ldg(ctr + k + t) + h * (double)n[t];
+                    if (k + t < D) zs[k + t] = cz[k + t] + h * (double)n[t];
             }
         }
         if (has_winv) {
@@ -170,89 +218,60 @@ cudaError_t launch_draw(const KdeDev* kde, int D, long long M, const double* u, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Order-preserving compaction: per-chunk counts -> exclusive scan -> scatter.
+// Order-preserving compaction in ONE pass over the flags (chained scan with decoupled look-back, Merrill & Garland 2016):
+// a CTA takes the next chunk of CP_CHUNK flags by ticket, counts its accepted rows, publishes the count, looks back over
+// its predecessors' published counts / prefixes for its output offset, and copies its accepted rows.  The flags are read
+// once (the three-kernel count / scan / scatter version read them twice and paid three launches).
+// Workspace (zeroed by launch_compact): ws[0] = ticket, ws[1 + c] = state of chunk c: bits 62..63 = 0 nothing yet,
+// 1 = the chunk's own count, 2 = inclusive prefix up to and including the chunk; bits 0..61 = the value.
 // ---------------------------------------------------------------------------------------------
 constexpr int CP_THREADS = 256;
-constexpr int CP_PER_THREAD = 8;
+constexpr int CP_PER_THREAD = 16;
 constexpr int CP_CHUNK = CP_THREADS * CP_PER_THREAD;
+constexpr unsigned long long CP_AGG = 1ull << 62, CP_PFX = 2ull << 62, CP_VAL = (1ull << 62) - 1;
 
 long long compact_nblocks(long long M) { return (M + CP_CHUNK - 1) / CP_CHUNK; }
+long long compact_ws_words(long long M) { return compact_nblocks(M) + 2; }           // ticket, chunk states, total
 
-__device__ __forceinline__ unsigned load_flags8(const unsigned char* __restrict__ flags, long long base, long long M)
+__device__ __forceinline__ unsigned nonzero_bytes4(unsigned v)      // bit t set <=> byte t of v is non-zero
 {
-    // bit t set <=> flags[base + t] != 0, t = 0..7
+    // per byte: (b | (b + 0x7f)) has its top bit set iff b != 0  (no carries across bytes: the low 7 bits are added alone)
+    const unsigned t = ((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v;
+    const unsigned h = t & 0x80808080u;
+    return ((h >> 7) & 1u) | ((h >> 14) & 2u) | ((h >> 21) & 4u) | ((h >> 28) & 8u);
+}
+
+__device__ __forceinline__ unsigned load_flags16(const unsigned char* __restrict__ flags, long long base, long long M)
+{
+    // bit t set <=> flags[base + t] != 0, t = 0..15
     unsigned m = 0;
-    if (base + 8 <= M && ((reinterpret_cast<uintptr_t>(flags + base) & 7) == 0)) {
-        const uint2 v = *reinterpret_cast<const uint2*>(flags + base);
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-            if ((v.x >> (8 * t)) & 0xff) m |= 1u << t;
-            if ((v.y >> (8 * t)) & 0xff) m |= 1u << (4 + t);
-        }
+    if (base + 16 <= M && ((reinterpret_cast<uintptr_t>(flags + base) & 15) == 0)) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(flags + base));
+        m = nonzero_bytes4(v.x) | (nonzero_bytes4(v.y) << 4) | (nonzero_bytes4(v.z) << 8) | (nonzero_bytes4(v.w) << 12);
     } else {
-        for (int t = 0; t < 8; t++) if (base + t < M && flags[base + t]) m |= 1u << t;
+        for (int t = 0; t < 16; t++) if (base + t < M && flags[base + t]) m |= 1u << t;
     }
     return m;
 }
 
 __global__ void __launch_bounds__(CP_THREADS)
-compact_count_kernel(const unsigned char* __restrict__ flags, long long M, unsigned long long* __restrict__ counts)
+compact_kernel(const unsigned char* __restrict__ flags, long long M, const unsigned char* __restrict__ rows,
+               int row_bytes, unsigned char* __restrict__ out, long long* __restrict__ out_index,
+               unsigned long long* __restrict__ ws, long long nb, unsigned long long* __restrict__ total_out)
 {
-    const long long base = (long long)blockIdx.x * CP_CHUNK + (long long)threadIdx.x * CP_PER_THREAD;
-    int c = base < M ? __popc(load_flags8(flags, base, M)) : 0;
-    __shared__ int wsum[CP_THREADS / 32];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
-        for (int w = 0; w < CP_THREADS / 32; w++) t += wsum[w];
-        counts[blockIdx.x] = (unsigned long long)t;
-    }
-}
-
-__global__ void __launch_bounds__(1024)
-compact_scan_kernel(unsigned long long* __restrict__ counts, long long nb, unsigned long long* __restrict__ total)
-{
-    // single CTA, in-place exclusive scan of nb chunk counts
-    __shared__ unsigned long long wtot[32];
-    __shared__ unsigned long long carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (long long b0 = 0; b0 < nb; b0 += 1024) {
-        const long long i = b0 + threadIdx.x;
-        const unsigned long long v = i < nb ? counts[i] : 0ull;
-        unsigned long long incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((threadIdx.x & 31) >= o) incl += t;
-        }
-        if ((threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = incl;
-        __syncthreads();
-        unsigned long long wbase = 0;
-        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) wbase += wtot[w];
-        const unsigned long long carry = carry_s;
-        if (i < nb) counts[i] = carry + wbase + incl - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = carry + wbase + incl;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *total = carry_s;
-}
-
-__global__ void __launch_bounds__(CP_THREADS)
-compact_scatter_kernel(const unsigned char* __restrict__ flags, long long M, const unsigned char* __restrict__ rows,
-                       int row_bytes, unsigned char* __restrict__ out, long long* __restrict__ out_index,
-                       const unsigned long long* __restrict__ offsets)
-{
-    const long long cbase = (long long)blockIdx.x * CP_CHUNK;
-    const long long base = cbase + (long long)threadIdx.x * CP_PER_THREAD;
-    const unsigned m = base < M ? load_flags8(flags, base, M) : 0u;
-    const int c = __popc(m);
     __shared__ int wsum[CP_THREADS / 32];
     __shared__ unsigned short sel[CP_CHUNK];             // accepted rows of this chunk (offset in the chunk), in input order
+    __shared__ long long s_chunk;
+    __shared__ unsigned long long s_excl;
+    volatile unsigned long long* state = ws + 1;
+    if (threadIdx.x == 0) s_chunk = (long long)atomicAdd(ws, 1ull);          // chunks start in index order: look-back cannot deadlock
+    __syncthreads();
+    const long long chunk = s_chunk;
+    if (chunk >= nb) return;
+    const long long cbase = chunk * CP_CHUNK;
+    const long long base = cbase + (long long)threadIdx.x * CP_PER_THREAD;
+    const unsigned m = base < M ? load_flags16(flags, base, M) : 0u;
+    const int c = __popc(m);
     int incl = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -262,15 +281,50 @@ compact_scatter_kernel(const unsigned char* __restrict__ flags, long long M, con
     if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
     __syncthreads();
     int wbase = 0, total = 0;
+#pragma unroll
     for (int w = 0; w < CP_THREADS / 32; w++) {
         if (w < (int)(threadIdx.x >> 5)) wbase += wsum[w];
         total += wsum[w];
     }
+    // publish this chunk's count, then look back (warp 0): sum the predecessors' counts until one carries a full prefix
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        if (lane == 0) {
+            state[chunk] = (chunk == 0 ? 2ull << 62 : 1ull << 62) | (unsigned long long)total;
+            __threadfence();
+        }
+        unsigned long long excl = 0;
+        long long j = chunk - 1;
+        while (j >= 0) {
+            const long long jj = j - lane;
+            unsigned long long v = 0;
+            bool done;
+            do {                                            // every lane's predecessor must have published something
+                v = jj >= 0 ? state[jj] : (2ull << 62);
+                done = (v >> 62) != 0ull;
+            } while (!__all_sync(0xffffffffu, done));
+            const unsigned pfx = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
+            const int stop = pfx ? __ffs(pfx) - 1 : 32;      // nearest predecessor with a full prefix (lane order = distance)
+            unsigned long long add = (lane <= stop) ? (v & CP_VAL) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);
+            excl += add;
+            if (pfx) break;
+            j -= 32;
+        }
+        if (lane == 0) {
+            if (chunk > 0) { __threadfence(); state[chunk] = CP_PFX | (excl + (unsigned long long)total); }
+            s_excl = excl;
+            if (chunk == nb - 1) *total_out = excl + (unsigned long long)total;
+        }
+    }
     int pos = wbase + incl - c;
-    for (int t = 0; t < 8; t++)
+#pragma unroll
+    for (int t = 0; t < CP_PER_THREAD; t++)
         if ((m >> t) & 1u) sel[pos++] = (unsigned short)(threadIdx.x * CP_PER_THREAD + t);
     __syncthreads();
-    const unsigned long long dst0 = offsets[blockIdx.x];
+    if (total == 0) return;
+    const unsigned long long dst0 = s_excl;
     if (out_index)
         for (int r = threadIdx.x; r < total; r += CP_THREADS) out_index[dst0 + r] = cbase + sel[r];
     if (!out) return;
@@ -280,9 +334,18 @@ compact_scatter_kernel(const unsigned char* __restrict__ flags, long long M, con
     const bool a4 = (row_bytes & 3) == 0 && ((reinterpret_cast<uintptr_t>(rows) | reinterpret_cast<uintptr_t>(out)) & 3) == 0;
     const int unit = a16 ? 16 : (a4 ? 4 : 1);
     const int upr = row_bytes / unit;
-    const long long nunits = (long long)total * upr;
-    for (long long i = threadIdx.x; i < nunits; i += CP_THREADS) {
-        const int r = (int)(i / upr), part = (int)(i % upr);
+    const int nunits = total * upr;
+    if (a16 && (upr & (upr - 1)) == 0) {                 // power-of-two pieces per row (8-D fp64 rows: 4): shifts, no divisions
+        const int sh = __ffs(upr) - 1;
+        for (int i = threadIdx.x; i < nunits; i += CP_THREADS) {
+            const int r = i >> sh, part = i & (upr - 1);
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(rows + (size_t)(cbase + sel[r]) * row_bytes) + part);
+            reinterpret_cast<uint4*>(out + (size_t)(dst0 + r) * row_bytes)[part] = v;
+        }
+        return;
+    }
+    for (int i = threadIdx.x; i < nunits; i += CP_THREADS) {
+        const int r = i / upr, part = i % upr;
         const unsigned char* sp = rows + (size_t)(cbase + sel[r]) * row_bytes + (size_t)part * unit;
         unsigned char* dp = out + (size_t)(dst0 + r) * row_bytes + (size_t)part * unit;
         if (a16) *reinterpret_cast<uint4*>(dp) = *reinterpret_cast<const uint4*>(sp);
@@ -291,19 +354,19 @@ compact_scatter_kernel(const unsigned char* __restrict__ flags, long long M, con
     }
 }
 
+// ws: compact_ws_words(M) words of scratch; the accepted count lands in ws[compact_ws_words(M) - 1] (= total)
 cudaError_t launch_compact(const unsigned char* flags, long long M, const void* rows, int elem_bytes,
                            long long ld, void* out, long long* out_index,
-                           unsigned long long* block_counts, unsigned long long* total, cudaStream_t st)
+                           unsigned long long* ws, unsigned long long* total, cudaStream_t st)
 {
     const long long nb = compact_nblocks(M);
     if (nb == 0) return cudaMemsetAsync(total, 0, sizeof(unsigned long long), st);
-    compact_count_kernel<<<(unsigned)nb, CP_THREADS, 0, st>>>(flags, M, block_counts);
-    compact_scan_kernel<<<1, 1024, 0, st>>>(block_counts, nb, total);
-    compact_scatter_kernel<<<(unsigned)nb, CP_THREADS, 0, st>>>(flags, M, reinterpret_cast<const unsigned char*>(rows),
-                                                                (int)(elem_bytes * ld),
-                                                                reinterpret_cast<unsigned char*>(out), out_index,
-                                                                block_counts);
-    count_launch(3);
+    cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)(nb + 1) * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    compact_kernel<<<(unsigned)nb, CP_THREADS, 0, st>>>(flags, M, reinterpret_cast<const unsigned char*>(rows),
+                                                        (int)(elem_bytes * ld), reinterpret_cast<unsigned char*>(out),
+                                                        out_index, ws, nb, total);
+    count_launch(1);
     return cudaGetLastError();
 }
 
