@@ -200,8 +200,9 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
     const bool cull = cull_enabled();
     // which culled kernel scores a job (a function of its dimension only, so that batching never changes the arithmetic):
     // the sorted-incidence pipeline (plan -> bucket -> evaluate -> finalize) where it is the fastest (measured on B200,
-    // profiles/r02o_*: d = 3..7), round 1's lanes = queries kernel for d <= 2 (dense incidence, already at the SFU
-    // roofline of its pairs) and per-query kernel for d >= 8.  skb_set_option("kernel", 1 / 2) forces either family.
+    // profiles/r04f_scan_routes.txt: d = 3..5), the lanes = queries kernel for d <= 2 (dense incidence, already at the SFU
+    // roofline of its pairs) and the per-query kernel for d >= 6 (since its tiles come straight from L2 it is ahead of the
+    // pipeline at d = 6 and 7 too: 21.1 vs 21.6 ms, 22.0 vs 22.6 ms).  skb_set_option("kernel", 1 / 2) forces either family.
     const int kopt = g_opt_kernel.load(std::memory_order_relaxed);
     bool use_sparse[SKB_MAX_JOBS];
     bool sparse = false;
@@ -209,7 +210,7 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
         const int D = jobs[j].h->hk.D;
         // (small training sets — up to two chunks of tiles — stay on the single-launch round-1 kernels: the pipeline's
         //  fixed cost of a dozen launches would dominate; like D, the tile count is a property of the fitted KDE)
-        use_sparse[j] = cull && (kopt == 2 || (kopt == 0 && D >= 3 && D <= 7 && jobs[j].h->hk.ntiles > 2 * CG * SG));
+        use_sparse[j] = cull && (kopt == 2 || (kopt == 0 && D >= 3 && D <= 5 && jobs[j].h->hk.ntiles > 2 * CG * SG));
         sparse |= use_sparse[j];
     }
     const bool fin_by_kernel = sparse && grouped;       // a group with a sparse member is finalized by the finalize kernel

@@ -174,20 +174,22 @@ skb_draw_kernel(const KdeDev* __restrict__ kde, long long M,
         }
         if (!bad) break;
     }
+    // streaming stores (evict-first): the output passes through L2 once and must not push the centre rows (zt64), the
+    // cumulative weights and their index out of it — the gathers of the next draws hit L2 instead of DRAM
     const long long o = rows ? rows[i] : i;
-    if (out_idx) out_idx[o] = idx;
+    if (out_idx) __stcs(out_idx + o, idx);
     if (out_x) {
         if ((D % 2 == 0) && ((ld_out & 1) == 0) && ((reinterpret_cast<uintptr_t>(out_x) & 15) == 0)) {
 #pragma unroll
-            for (int c = 0; c < D; c += 2) *reinterpret_cast<double2*>(out_x + o * ld_out + c) = make_double2(x[c], x[c + 1]);
+            for (int c = 0; c < D; c += 2) __stcs(reinterpret_cast<double2*>(out_x + o * ld_out + c), make_double2(x[c], x[c + 1]));
         } else {
 #pragma unroll
-            for (int c = 0; c < D; c++) out_x[o * ld_out + c] = x[c];
+            for (int c = 0; c < D; c++) __stcs(out_x + o * ld_out + c, x[c]);
         }
     }
     if (out_z) {
 #pragma unroll
-        for (int k = 0; k < D; k++) out_z[o * D + k] = zs[k];
+        for (int k = 0; k < D; k++) __stcs(out_z + o * D + k, zs[k]);
     }
     if (out_flag) out_flag[o] = bad ? 1 : 0;
     if (n_flagged) {

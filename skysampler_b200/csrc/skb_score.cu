@@ -66,6 +66,9 @@ namespace skb {
 #ifndef SKB_PQ_MINB
 #define SKB_PQ_MINB 22        // launch bound (CTAs per SM) of the PQ kernel for D <= 8 (96 registers)
 #endif
+#ifndef SKB_PQ_MINB_TOP
+#define SKB_PQ_MINB_TOP 16    // D > 12 (128 registers)
+#endif
 #ifndef SKB_PQ_MINB_HI
 #define SKB_PQ_MINB_HI 20     // same for 8 < D <= 12 (80 registers); D > 12 keeps 16 (128 registers)
 #endif
@@ -82,34 +85,55 @@ constexpr int PQ_ROW = 33;                        // part[query][lane], rows pad
 #ifndef SKB_PQ_SLACK
 #define SKB_PQ_SLACK 3        // a lane term >= 2^(SLACK - REF_BIAS) (a point that much closer than the reference) recentres
 #endif
-#ifndef SKB_PQ_LDG
-#define SKB_PQ_LDG 1          // 1: a lane reads its two points of a tile straight from L2 (coalesced LDG.64 rows), no smem ring
-#endif
-#ifndef SKB_PQ_PREFETCH
-#define SKB_PQ_PREFETCH 0     // (LDG mode) 1: the next work-list entry's points are loaded before this entry's pair loop
-#endif
 static_assert(PQ_CH <= 32 && PQ_CAP <= 256 && SG == 16, "PQ chunk layout");
 __host__ __device__ constexpr bool pq_mode(int D, int Q) { return SKB_PQ && D >= SKB_PQ_MIN_D && Q == 1 && tile_points(D) == 64; }
 __host__ __device__ constexpr int pq_qstride(int D) { return (D + 4) & ~3; }          // floats per query row: z[0..D), -m, padding to 16 B
 __host__ __device__ constexpr size_t pq_smem_bytes(int D)
 {
-    return (SKB_PQ_LDG ? (size_t)0 : (size_t)SKB_NSTAGE_PQ * stage_floats(D) * 4 + (size_t)SKB_NSTAGE_PQ * 16) +
-           (size_t)32 * pq_qstride(D) * 4 + (size_t)32 * PQ_ROW * 4 + (size_t)PQ_CAP * 4 + (size_t)PQ_CAP + 16;
+    return (size_t)32 * pq_qstride(D) * 4 + (size_t)32 * PQ_ROW * 4 + (size_t)PQ_CAP * 4 + (size_t)PQ_CAP + 16;
+}
+
+// shared memory through 32-bit shared-window addresses
+__device__ __forceinline__ float4 lds128(uint32_t a)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t a)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v)
+{
+    asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory");
+}
+
+// one query row (z[0..D), -m, padding) from shared memory
+template <int D>
+__device__ __forceinline__ void pq_load_row(uint32_t qrow, float (&r)[pq_qstride(D)])
+{
+    constexpr int QS = pq_qstride(D);
+#pragma unroll
+    for (int k = 0; k < QS; k += 4) {
+        if (k + 4 <= D + 1 || k < D + 1) {
+            const float4 v = lds128(qrow + 4u * k);
+            r[k] = v.x; r[k + 1] = v.y; r[k + 2] = v.z; r[k + 3] = v.w;
+        }
+    }
 }
 
 // acc - m for this lane's two points against the query row in shared memory.  The row holds plain floats:
 // ptxas folds pk(z, z) into the scalar-broadcast operand form of FADD2 / FFMA2 (`R.F32`), so duplicated
 // pairs would only cost shared memory, LDS slots and registers.
 template <int D>
-__device__ __forceinline__ void pq_acc(const float* __restrict__ qrow, const u64 (&p2)[D], float& a0, float& a1)
+__device__ __forceinline__ void pq_acc(uint32_t qrow, const u64 (&p2)[D], float& a0, float& a1)
 {
     constexpr int QS = pq_qstride(D);
     float r[QS];
-#pragma unroll
-    for (int k = 0; k < QS; k += 4) {
-        const float4 v = *reinterpret_cast<const float4*>(qrow + k);
-        r[k] = v.x; r[k + 1] = v.y; r[k + 2] = v.z; r[k + 3] = v.w;
-    }
+    pq_load_row<D>(qrow, r);
     u64 acc = pk(r[D], r[D]);
 #pragma unroll
     for (int k = 0; k < D; k++) {
@@ -420,16 +444,13 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
 }
 
 template <int D, bool STATS>
-__global__ void __launch_bounds__(32, D <= 8 ? SKB_PQ_MINB : (D <= 12 ? SKB_PQ_MINB_HI : 16))
+__global__ void __launch_bounds__(32, D <= 8 ? SKB_PQ_MINB : (D <= 12 ? SKB_PQ_MINB_HI : SKB_PQ_MINB_TOP))
 skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
 {
     constexpr int Q = 1;
-    constexpr bool LDG = SKB_PQ_LDG != 0;
     constexpr int TN = tile_points(D);
     constexpr int QS = pq_qstride(D);
     constexpr int STAGE_FLOATS = stage_floats(D);
-    constexpr uint32_t STAGE_BYTES = STAGE_FLOATS * sizeof(float);
-    constexpr int NSTAGE = SKB_NSTAGE_PQ;
     constexpr unsigned FULL = 0xffffffffu;
     static_assert(TN == 64 && NT == 32, "PQ: one warp per CTA, two tile points per lane");
 
@@ -439,10 +460,7 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
     if (qbase >= M || (int)blockIdx.z >= job.nsplit) return;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* stages = reinterpret_cast<float*>(smem_raw);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (LDG ? (size_t)0 : (size_t)NSTAGE * STAGE_BYTES));
-    uint64_t* empty_bar = full_bar + (LDG ? 0 : NSTAGE);
-    float* rows = reinterpret_cast<float*>(empty_bar + (LDG ? 0 : NSTAGE));       // 32 query rows: z[0..D), -m
+    float* rows = reinterpret_cast<float*>(smem_raw);                 // 32 query rows: z[0..D), -m
     float* part = rows + 32 * QS;                                     // part[query][lane], rows of PQ_ROW words
     unsigned* lmask = reinterpret_cast<unsigned*>(part + 32 * PQ_ROW);   // work list: query mask ...
     unsigned char* ltile = reinterpret_cast<unsigned char*>(lmask + PQ_CAP);   // ... and tile offset in the chunk
@@ -454,13 +472,6 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
     const int nsplit = job.nsplit;
     const int t0 = (int)(((long long)ntiles * blockIdx.z) / nsplit);
     const int t1 = (int)(((long long)ntiles * (blockIdx.z + 1)) / nsplit);
-
-    if (!LDG && lane == 0) {
-#pragma unroll
-        for (int s = 0; s < NSTAGE; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_fence_init();
-    }
-    __syncwarp();
 
     float q2[Q][D];
     load_queries<D, Q>(job, kde, qbase, lane, M, q2);
@@ -476,8 +487,11 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
     for (int k = 0; k < D; k++) rows[lane * QS + k] = q2[0][k];
     rows[lane * QS + D] = -mref[0];
     for (int l = 0; l < 32; l++) part[l * PQ_ROW + lane] = 0.f;
-    float* const mypart = part + lane;                                 // + query * PQ_ROW
     __syncwarp();
+    // the hot loops address the rows and the partials through 32-bit shared-window addresses (ld/st.shared): with generic
+    // pointers ptxas re-derived the window base (S2R SR_CgaCtaId + 4 ALU ops) inside every loop to save a register
+    const uint32_t rows_s = smem_u32(rows);
+    const uint32_t mypart_s = smem_u32(part) + 4u * (uint32_t)lane;    // + query * PQ_ROW * 4
 
     const float* __restrict__ cbx = kde->cboxes;
     const float* __restrict__ sbx = kde->sboxes;
@@ -487,15 +501,6 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
     unsigned n_rerun = 0, n_visited = 0;
     unsigned long long n_pairs = 0;
     int epoch_cur = -1;
-    unsigned it = 0;                                   // tiles consumed so far (ring position)
-
-    // request tile `t` into the ring slot of consumption index g (lane 0 only)
-    auto request = [&](unsigned g, int t) {
-        const int sp = (int)(g % NSTAGE);
-        if (g >= (unsigned)NSTAGE) mbar_wait(&empty_bar[sp], ((g / NSTAGE) - 1u) & 1u);
-        mbar_expect_tx(&full_bar[sp], STAGE_BYTES);
-        tma_bulk_g2s(stages + (size_t)sp * STAGE_FLOATS, gtiles + (size_t)t * STAGE_FLOATS, STAGE_BYTES, &full_bar[sp]);
-    };
 
     const int s_first = (t0 / SG / PQ_CH) * PQ_CH, s_end = (t1 + SG - 1) / SG;   // chunk aligned; tiles outside [t0, t1) are masked
 #pragma unroll 1
@@ -573,16 +578,15 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
                 const bool on = qm != 0u;
                 const int i = on ? 31 - __clz(qm) : 0;
                 qm &= ~(1u << i);                                         // 0 stays 0
-                const float* qrow = rows + i * QS;
+                float r[QS];
+                pq_load_row<D>(rows_s + (uint32_t)i * (QS * 4), r);
                 float lb = 0.f;
 #pragma unroll
                 for (int k = 0; k < D; k++) {
-                    const float zq = qrow[k];
-                    const float gap = fmaxf(fmaxf(lo[k] - zq, zq - hi[k]), 0.f);
+                    const float gap = fmaxf(fmaxf(lo[k] - r[k], r[k] - hi[k]), 0.f);
                     lb = fmaf(gap, gap, lb);
                 }
-                const float negm = qrow[D];
-                if (on && (!cull || !(lb + negm > CULL_MARGIN))) tmask |= 1u << i;
+                if (on && (!cull || !(lb + r[D] > CULL_MARGIN))) tmask |= 1u << i;
             }
             const unsigned nz = __ballot_sync(FULL, tmask != 0u);
             if (tmask) {
@@ -596,63 +600,30 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
         if (cnt == 0) continue;
         if constexpr (STATS) n_visited += (unsigned)cnt;
 
-        // ---- (3) stream the work list.  LDG mode: every lane reads its two points of a tile straight from L2 (one coalesced
-        //          256-byte row per dimension), no shared-memory ring and no barriers; ring mode: 1-D TMA copies ----
+        // ---- (3) stream the work list: every lane reads its two points of a tile straight from L2 (one coalesced
+        //          256-byte row per dimension, LDG.64) and keeps them in registers while the tile's query mask is walked:
+        //          no shared-memory staging, no barriers (the TMA ring this replaces cost ~60 issue slots per tile) ----
         const int tchunk = s_base * SG;
-        if (!LDG && lane == 0) {
-            const int npre = cnt < NSTAGE ? cnt : NSTAGE;
-            for (int e = 0; e < npre; e++) request(it + (unsigned)e, tchunk + ltile[e]);
-        }
-        u64 p2[D];
-        float w0, w1;
-        auto fetch = [&](int t, u64 (&pp)[D], float& ww0, float& ww1) {
-            const float* __restrict__ tile = gtiles + (size_t)t * STAGE_FLOATS + 2 * lane;
-#pragma unroll
-            for (int k = 0; k < D; k++) pp[k] = __ldg(reinterpret_cast<const u64*>(tile + k * TN));
-            upk(__ldg(reinterpret_cast<const u64*>(tile + D * TN)), ww0, ww1);
-        };
-#if SKB_PQ_LDG && SKB_PQ_PREFETCH
-        u64 pn[D];
-        float wn0, wn1;
-        fetch(tchunk + ltile[0], pn, wn0, wn1);
-#endif
 #pragma unroll 1
-        for (int e = 0; e < cnt; e++, it++) {
-            const int s = (int)(it % NSTAGE);
+        for (int e = 0; e < cnt; e++) {
             unsigned mask = lmask[e];
             const int tcur = tchunk + ltile[e];
-
             const int epoch = tcur >> PQ_EPOCH_SHIFT;
             if (epoch != epoch_cur) {
                 if (epoch_cur >= 0) { __syncwarp(); S[0] += pq_fold_row(part, lane); __syncwarp(); }
                 epoch_cur = epoch;
             }
-            // this lane's two points of the tile
-            if constexpr (LDG) {
-#if SKB_PQ_LDG && SKB_PQ_PREFETCH
+            u64 p2[D];
+            float w0, w1;
+            {
+                const float* __restrict__ tile = gtiles + (size_t)tcur * STAGE_FLOATS + 2 * lane;
 #pragma unroll
-                for (int k = 0; k < D; k++) p2[k] = pn[k];
-                w0 = wn0; w1 = wn1;
-                if (e + 1 < cnt) fetch(tchunk + ltile[e + 1], pn, wn0, wn1);
-#else
-                fetch(tcur, p2, w0, w1);
-#endif
-            } else {
-                mbar_wait(&full_bar[s], (it / NSTAGE) & 1u);
-                const float* tile = stages + (size_t)s * STAGE_FLOATS;
-#pragma unroll
-                for (int k = 0; k < D; k++) p2[k] = *reinterpret_cast<const u64*>(tile + k * TN + 2 * lane);
-                upk(*reinterpret_cast<const u64*>(tile + D * TN + 2 * lane), w0, w1);
-                // the tile now lives in registers: hand the stage back and request the tile NSTAGE entries ahead
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&empty_bar[s]);
-                    if (e + NSTAGE < cnt) request(it + (unsigned)NSTAGE, tchunk + ltile[e + NSTAGE]);
-                }
+                for (int k = 0; k < D; k++) p2[k] = __ldg(reinterpret_cast<const u64*>(tile + k * TN));
+                upk(__ldg(reinterpret_cast<const u64*>(tile + D * TN)), w0, w1);
             }
             if constexpr (STATS) n_pairs += 2u * __popc(mask);
 
-            // rare: a point >= 8 binades closer than the reference was built for (or a NaN row) — fold the
+            // rare: a point >= SLACK binades closer than the reference was built for (or a NaN row) — fold the
             // row, move the query's reference to the tile's closest point, re-evaluate
             auto recentre = [&](int i, float a0, float a1) -> float {
                 float am = fminf(a0 + fminf(-__log2f(w0), LW_CAP), a1 + fminf(-__log2f(w1), LW_CAP));   // weighted exponents
@@ -667,10 +638,10 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
                         S[0] = ldexp(S[0], (int)fmaxf(delta, -4000.f));
                         mref[0] += delta;
                         nm2[0] = -mref[0];
-                        rows[i * QS + D] = -mref[0];
+                        sts32(rows_s + (uint32_t)(i * QS + D) * 4u, -mref[0]);
                     }
                     __syncwarp();
-                    pq_acc<D>(rows + i * QS, p2, a0, a1);
+                    pq_acc<D>(rows_s + (uint32_t)i * (QS * 4), p2, a0, a1);
                     return __fmaf_rn(w1, ex2_neg(a1), __fmul_rn(w0, ex2_neg(a0)));
                 }
                 if (lane == i) S[0] = NAN;                                  // NaN / inf query row: propagate
@@ -685,9 +656,9 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
 #pragma unroll
                 for (int n = 0; n < NQ; n++) { idx[n] = 31 - __clz(mask); mask ^= 1u << idx[n]; }   // highest set bit: one FLO, no BREV
 #pragma unroll
-                for (int n = 0; n < NQ; n++) pa[n] = mypart[idx[n] * PQ_ROW];   // issued early: off the critical path
+                for (int n = 0; n < NQ; n++) pa[n] = lds32(mypart_s + (uint32_t)idx[n] * (PQ_ROW * 4));   // issued early: off the critical path
 #pragma unroll
-                for (int n = 0; n < NQ; n++) pq_acc<D>(rows + idx[n] * QS, p2, a0[n], a1[n]);
+                for (int n = 0; n < NQ; n++) pq_acc<D>(rows_s + (uint32_t)idx[n] * (QS * 4), p2, a0[n], a1[n]);
                 bool bad = false;
 #pragma unroll
                 for (int n = 0; n < NQ; n++) {
@@ -699,11 +670,11 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
                     for (int n = 0; n < NQ; n++)
                         if (__any_sync(FULL, !(t[n] < PQ_LIMIT))) {
                             t[n] = recentre(idx[n], a0[n], a1[n]);
-                            pa[n] = mypart[idx[n] * PQ_ROW];
+                            pa[n] = lds32(mypart_s + (uint32_t)idx[n] * (PQ_ROW * 4));
                         }
                 }
 #pragma unroll
-                for (int n = 0; n < NQ; n++) mypart[idx[n] * PQ_ROW] = pa[n] + t[n];
+                for (int n = 0; n < NQ; n++) sts32(mypart_s + (uint32_t)idx[n] * (PQ_ROW * 4), pa[n] + t[n]);
             };
             if constexpr (SKB_PQ_UNROLL >= 4 || D <= SKB_PQ_UNROLL4_MAX_D)
                 while (__popc(mask) >= 4) eval(std::integral_constant<int, 4>{});
