@@ -93,6 +93,17 @@ __host__ __device__ constexpr size_t pq_smem_bytes(int D)
     return (size_t)32 * pq_qstride(D) * 4 + (size_t)32 * PQ_ROW * 4 + (size_t)PQ_CAP * 4 + (size_t)PQ_CAP + 16;
 }
 
+// index of the highest set bit of a non-zero mask, and the mask without it (FLO + BMSK + LOP3)
+__device__ __forceinline__ int pop_top_bit(unsigned& mask)
+{
+    int idx;
+    unsigned bit;
+    asm("bfind.u32 %0, %1;" : "=r"(idx) : "r"(mask));
+    asm("bmsk.clamp.b32 %0, %1, 1;" : "=r"(bit) : "r"(idx));
+    mask ^= bit;
+    return idx;
+}
+
 // shared memory through 32-bit shared-window addresses
 __device__ __forceinline__ float4 lds128(uint32_t a)
 {
@@ -576,8 +587,8 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
             unsigned tmask = 0u;
             while (__any_sync(FULL, qm != 0u)) {
                 const bool on = qm != 0u;
-                const int i = on ? 31 - __clz(qm) : 0;
-                qm &= ~(1u << i);                                         // 0 stays 0
+                int i = pop_top_bit(qm);                                  // an empty mask stays empty (bfind gives -1, bmsk clamps to 0)
+                i = on ? i : 0;
                 float r[QS];
                 pq_load_row<D>(rows_s + (uint32_t)i * (QS * 4), r);
                 float lb = 0.f;
@@ -654,7 +665,7 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
                 int idx[NQ];
                 float pa[NQ], a0[NQ], a1[NQ], t[NQ];
 #pragma unroll
-                for (int n = 0; n < NQ; n++) { idx[n] = 31 - __clz(mask); mask ^= 1u << idx[n]; }   // highest set bit: one FLO, no BREV
+                for (int n = 0; n < NQ; n++) idx[n] = pop_top_bit(mask);
 #pragma unroll
                 for (int n = 0; n < NQ; n++) pa[n] = lds32(mypart_s + (uint32_t)idx[n] * (PQ_ROW * 4));   // issued early: off the critical path
 #pragma unroll
