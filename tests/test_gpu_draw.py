@@ -152,3 +152,65 @@ def test_compaction_preserves_order(m, frac):
     assert cnt.value == k
     assert np.array_equal(out[:k].cpu().numpy(), rows[flags.astype(bool)])
     assert np.array_equal(oi[:k].cpu().numpy(), np.nonzero(flags)[0])
+
+
+@pytest.mark.parametrize("m,frac,width,dtype,shift", [
+    (4096, 0.5, 8, np.float64, 0),            # exactly one chunk
+    (4097, 1.0, 8, np.float64, 0),            # one row into the second chunk
+    (40 * 4096 + 13, 0.02, 8, np.float64, 0),  # look-back past one 32-chunk window
+    (300 * 4096 + 5, 0.0, 4, np.float64, 0),   # nothing accepted over many chunks
+    (70 * 4096, 0.93, 3, np.float32, 0),       # fp32 rows of 12 bytes (4-byte copy path)
+    (50001, 0.4, 2, np.float64, 3),            # flags not 16-byte aligned (byte-wise flag loads)
+])
+def test_single_pass_compaction_chunks_lookback_and_alignment(m, frac, width, dtype, shift):
+    """The chained-scan compaction (one pass over the flags, decoupled look-back) against numpy's samples[inds]
+    (emulator.py:746-747): chunk boundaries, long look-back chains, odd row widths, unaligned flags, device count."""
+    import torch
+    from skysampler_b200 import _cabi
+    rs = np.random.RandomState(m % 1000 + width)
+    flags = (rs.rand(m) < frac).astype(np.uint8)
+    flags[flags > 0] = rs.randint(1, 256, size=int(flags.sum())).astype(np.uint8)      # any non-zero byte is "accepted"
+    rows = rs.normal(size=(m, width)).astype(dtype)
+    fbuf = torch.zeros(m + 16, dtype=torch.uint8, device="cuda")
+    ft = fbuf[shift:shift + m]
+    ft.copy_(torch.from_numpy(flags))
+    rt = torch.from_numpy(rows).cuda()
+    out = torch.full((m, width), -1.0, dtype=rt.dtype, device="cuda")
+    oi = torch.full((m,), -1, dtype=torch.int64, device="cuda")
+    cnt_dev = torch.full((1,), -5, dtype=torch.int64, device="cuda")
+    for _ in range(2):                                            # twice: the workspace is recycled by the stream-ordered pool
+        _cabi.check(_cabi.lib().skb_compact(_cabi.ptr(ft), m, _cabi.ptr(rt), 1 if dtype == np.float32 else 0, width,
+                                            _cabi.ptr(out), _cabi.ptr(oi),
+                                            C.cast(C.c_void_p(cnt_dev.data_ptr()), C.POINTER(C.c_int64)), None))
+    k = int((flags != 0).sum())
+    assert int(cnt_dev.item()) == k
+    assert np.array_equal(out[:k].cpu().numpy(), rows[flags != 0])
+    assert np.array_equal(oi[:k].cpu().numpy(), np.nonzero(flags)[0])
+    assert bool((out[k:] == -1.0).all())                          # nothing written past the accepted rows
+
+
+def test_bracketed_centre_search_equals_searchsorted_on_hard_weights():
+    """The draw brackets its search of the cumulative weights with a bucket index (skb_sample.cu: cs_index_kernel);
+    the selected centre must still be np.searchsorted(cumsum, u * cumsum[-1]) (sklearn _kde.py:345-347) bit for bit:
+    zero weights, 12 decades of dynamic range, uniforms on and next to every bucket edge, u = 0 and u -> 1."""
+    from skysampler_b200 import GaussianKDE, _cabi
+    rs = np.random.RandomState(5)
+    n, d = 20011, 3
+    x = rs.normal(size=(n, d))
+    w = 10.0 ** rs.uniform(-9, 3, size=n)
+    w[rs.rand(n) < 0.3] = 0.0
+    w[:50] = 0.0; w[-70:] = 0.0; w[5000:5600] = 0.0
+    kde = GaussianKDE(0.2).fit(x, sample_weight=w)
+    cs = np.cumsum(w)
+    edges = np.arange(n + 1) / float(n)
+    u = np.concatenate([edges[:-1], np.nextafter(edges[1:], 0), np.nextafter(edges[:-1], 1), rs.uniform(size=30000),
+                        [0.0, np.nextafter(1.0, 0), 0.5]])
+    m = len(u)
+    z = np.zeros((m, d))
+    idx = np.empty(m, dtype=np.int64); xz = np.empty((m, d)); xr = np.empty((m, d))
+    _cabi.check(_cabi.lib().skb_draw(kde._handle(), m, _cabi.ptr(u), _cabi.ptr(z), 0, 0, None, -1, 0.0, 0.0, 1,
+                                     _cabi.ptr(idx), _cabi.ptr(xr), d, _cabi.ptr(xz), None, None, None))
+    want = np.minimum(np.searchsorted(cs, u * cs[-1]), n - 1)
+    assert np.array_equal(idx, want)
+    assert np.all(w[idx[u > 0]] > 0)
+    kde.close()
