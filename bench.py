@@ -460,7 +460,7 @@ def run_ours(args):
                 traffic = None
         roof = {
             # bound: the FP32 FMA pipe (with the SFU as second limit) — not HBM, not tensor cores
-            "bound": "fp32", "kernel": "skb::skb_score_pq_kernel<8> (both KDEs of the group in one launch)",
+            "bound": "fp32", "kernel": "skb::skb_score_pq_kernel<8, false> (both KDEs of the group in one launch)",
             "achieved": ach_exec * flop_pair / 1e12, "peak": peak_pairs * flop_pair / 1e12, "unit": "TFLOP/s",
             "frac": ach_exec / peak_pairs, "traffic": traffic,
             "definition": "achieved = pairs the launch actually EVALUATES (counted by the kernel with diagnostics on, same "
