@@ -672,6 +672,7 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
         const size_t o_tiles = carve(tile_bytes);
         const size_t o_boxes = carve((size_t)hk.ntiles * 2 * d * sizeof(float));
         const size_t o_sb = carve((size_t)(hk.nsuper + hk.nchunk) * 2 * d * sizeof(float));   // super-boxes, then chunk boxes
+        const size_t o_mom = carve(d == 1 ? (size_t)hk.ntiles * 12 * sizeof(float) : 0);
         const size_t o_dk = carve(sizeof(KdeDev));
         SKB_CUDA_C(cudaMalloc(&k->slab, off));
         char* base = reinterpret_cast<char*>(k->slab);
@@ -682,6 +683,7 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
         k->boxes = reinterpret_cast<float*>(base + o_boxes);
         k->sboxes = reinterpret_cast<float*>(base + o_sb);
         k->dk = reinterpret_cast<KdeDev*>(base + o_dk);
+        hk.mom = d == 1 ? reinterpret_cast<float*>(base + o_mom) : nullptr;
     }
     if (w) {
         SKB_CUDA_C(cudaMemcpyAsync(k->cumsum, cs.data(), (size_t)N * 8, cudaMemcpyHostToDevice, st));
@@ -715,6 +717,7 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
     SKB_CUDA_C(launch_fit(d_train, train_dtype == SKB_F32, N, d, ld_train, train_is_whitened, k->dk, k->zt64, st));
     SKB_CUDA_C(launch_kd_order(k->zt64, d_w, N, nv, d, hk.c, d_perm, k->dk, st));     // also fills dk->glo / ghi
     SKB_CUDA_C(launch_pack(k->zt64, d_perm, d, hk.c, d_w, 1.0 / wmax, k->tiles, hk.ntiles, k->boxes, k->sboxes, cboxes, st));
+    SKB_CUDA_C(launch_moments(k->tiles, k->boxes, hk.ntiles, const_cast<float*>(hk.mom), st));
     SKB_CUDA_C(cudaEventRecord(ev1, st));
     SKB_CUDA_C(cudaMemcpyAsync(hk.glo, reinterpret_cast<char*>(k->dk) + offsetof(KdeDev, glo), sizeof(hk.glo) + sizeof(hk.ghi),
                                cudaMemcpyDeviceToHost, st));

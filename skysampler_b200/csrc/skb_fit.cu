@@ -106,6 +106,56 @@ __global__ void skb_groupbox_kernel(const float* __restrict__ boxes, int D, int 
     out[(size_t)s * 2 * D + D + k] = hi;
 }
 
+// D == 1: far-field record of every tile.  With prescaled coordinates a pair term is 2^-(q - x)^2; about the tile's centre c
+// (s = q - c, t = x - c):  2^-(s - t)^2 = 2^-(s^2) * e^(2 ln2 s t) * 2^-(t^2), so the whole tile contributes
+//     2^-(s^2) * sum_n B_n s^n,   B_n = (2 ln2)^n / n! * sum_j w_j t_j^n 2^-(t_j^2)
+// and the series is cut after n = 5 when 2 ln2 |s| r <= 1/4 (r = the tile's half width): relative remainder < 6e-7 of the
+// tile's own (positive) contribution.  One warp per tile, fp64 sums.
+__global__ void skb_moment_kernel(const float* __restrict__ tiles, const float* __restrict__ boxes, int ntiles,
+                                  float* __restrict__ mom)
+{
+    constexpr int TN = tile_points(1);
+    const int t = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
+    const int lane = threadIdx.x & 31;
+    if (t >= ntiles) return;
+    const float* tile = tiles + (size_t)t * stage_floats(1);
+    const float lo = boxes[2 * t], hi = boxes[2 * t + 1];
+    const float c = 0.5f * lo + 0.5f * hi;
+    double a[6] = {0, 0, 0, 0, 0, 0};
+    for (int o = lane; o < TN; o += 32) {
+        const double w = (double)tile[TN + o];
+        if (!(w > 0.0)) continue;
+        const double tt = (double)tile[o] - (double)c;
+        double term = w * exp2(-tt * tt);
+#pragma unroll
+        for (int n = 0; n < 6; n++) { a[n] += term; term *= tt; }
+    }
+#pragma unroll
+    for (int n = 0; n < 6; n++)
+        for (int s = 16; s > 0; s >>= 1) a[n] += __shfl_xor_sync(0xffffffffu, a[n], s);
+    if (lane == 0) {
+        float* r = mom + (size_t)t * 12;
+        const bool valid = lo <= hi;
+        r[0] = lo; r[1] = hi; r[2] = valid ? c : 0.f;
+        r[3] = valid ? fmaxf(hi - c, c - lo) * 1.000001f : 0.f;
+        const double L2 = 2.0 * 0.693147180559945309417232121458;
+        double f = 1.0;
+        for (int n = 0; n < 6; n++) {
+            r[4 + n] = valid ? (float)(a[n] * f) : 0.f;
+            f *= L2 / (double)(n + 1);
+        }
+        r[10] = 0.f; r[11] = 0.f;
+    }
+}
+
+cudaError_t launch_moments(const float* tiles, const float* boxes, int ntiles, float* mom, cudaStream_t st)
+{
+    if (!mom || ntiles <= 0) return cudaSuccess;
+    skb_moment_kernel<<<(unsigned)((ntiles + 7) / 8), 256, 0, st>>>(tiles, boxes, ntiles, mom);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_fit(const void* train, int f32, long long N, int D, long long ld, int is_whitened,
                        const KdeDev* kde_dev, double* zt64, cudaStream_t st)
 {

@@ -93,6 +93,7 @@ struct KdeDev {
     const float* tiles;      // [ntiles][D+2][tile_points(D)]
     const double* zt64;      // [N][D] whitened fp64 rows (draw centres)
     const double* cumsum_w;  // [N] sequential fp64 cumsum (NULL for unweighted)
+    const float* mom;        // D == 1 only: [ntiles][12] far-field record of a tile: lo, hi, centre, radius, B0..B5, 0, 0
     const int* cs_index;     // [cs_buckets + 1] cs_index[b] = searchsorted(cumsum_w, b / cs_buckets * cumsum_w[N-1]): brackets the draw's search
     int cs_buckets;
     const float* boxes;      // [ntiles][2][D] lo / hi of the packed fp32 coordinates
@@ -227,6 +228,7 @@ cudaError_t launch_draw(const KdeDev* kde, int D, long long M, const double* u, 
                         int rcol, double rmin, double rmax, int max_attempts,
                         long long* out_idx, double* out_x, long long ld_out, double* out_z,
                         unsigned char* out_flag, unsigned long long* n_flagged, cudaStream_t st);
+cudaError_t launch_moments(const float* tiles, const float* boxes, int ntiles, float* mom, cudaStream_t st);
 cudaError_t launch_cs_index(const double* cumsum, long long N, int* index, int buckets, cudaStream_t st);
 cudaError_t launch_compact(const unsigned char* flags, long long M, const void* rows, int elem_bytes,
                            long long ld, void* out, long long* out_index,

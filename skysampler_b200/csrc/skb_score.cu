@@ -706,12 +706,159 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
     finish_queries<D, Q>(L, job, qbase, lane, M, mref, S, s_last);
 }
 
+// ---------------------------------------------------------------------------------------------
+// D == 1.  One coordinate means the tiles are SORTED intervals, and a 128-point tile is far narrower than the
+// kernel: a tile's 128 terms collapse into one exponential times a degree-5 polynomial in s = q - centre
+// (skb_fit.cu: skb_moment_kernel; cut when 2 ln2 |s| r <= 1/4, relative remainder < 6e-7 of the tile's own positive
+// contribution).  A query needs 14-37 % of ALL points in 1-D, so the pair loop sat on the MUFU.EX2 roofline (95 ms for
+// 1e6 x 2^20); per tile this is ~12 instructions instead of 128 exponentials.
+//   lanes = queries (Morton order = sorted, so a warp's queries walk the same tiles and every table load is a broadcast);
+//   reference exponent: the nearest point is in the tile that holds q or the one before it (binary search over the tile
+//     intervals, then an exact weighted scan of the home tile and its two neighbours) — the true weighted minimum is
+//     within 64 binades of it (LW_CAP), the fp32 window has 216: no term can overflow and there is no re-centring;
+//   window: the same box test as everywhere (a tile whose interval is > 128 binades past the reference holds only terms
+//     that flush), evaluated per query on a range found by two binary searches; tiles too wide for the series (sparse
+//     tails) are evaluated point by point for exactly the queries that need it;
+//   fp32 tile values are folded into the query's fp64 sum at fixed tile indices.
+// Everything is a function of the query and the fitted KDE alone: results do not depend on the batch.
+// ---------------------------------------------------------------------------------------------
+constexpr int D1_NT = 128;
+constexpr int D1_FOLD = 64;
+constexpr float D1_SR_MAX = 0.25f / 1.3862943611198906f;      // |s| r <= 1/4 / (2 ln 2)
+
+__global__ void __launch_bounds__(D1_NT)
+skb_score_d1_kernel(const __grid_constant__ ScoreLaunch L)
+{
+    constexpr int TN = tile_points(1);
+    constexpr int STAGE_FLOATS = stage_floats(1);
+    constexpr unsigned FULL = 0xffffffffu;
+    const ScoreJob& job = L.jobs[blockIdx.y];
+    const long long M = job.M;
+    const long long qbase = (long long)blockIdx.x * D1_NT;
+    if (qbase >= M || (int)blockIdx.z >= job.nsplit) return;
+    __shared__ int s_last[D1_NT / FB];
+
+    const int tid = threadIdx.x;
+    const KdeDev* __restrict__ kde = job.kde;
+    const int ntiles = kde->ntiles;
+    const int nsplit = job.nsplit;
+    const int t0 = (int)(((long long)ntiles * blockIdx.z) / nsplit);
+    const int t1 = (int)(((long long)ntiles * (blockIdx.z + 1)) / nsplit);
+    const float* __restrict__ bx = kde->boxes;                      // [tile][lo, hi]
+    const float* __restrict__ gtiles = kde->tiles;
+    const float4* __restrict__ mom = reinterpret_cast<const float4*>(kde->mom);
+    const bool has_w = kde->has_w != 0;
+    const float ref_bias = kde->ref_bias;
+
+    float q2[1][1];
+    load_queries<1, 1>(job, kde, qbase, tid, M, q2);
+    const float zq = q2[0][0];
+
+    // ---- reference exponent from the nearest point: home tile = first interval that ends at or after q ----
+    int th;
+    {
+        int lo = 0, hi = ntiles - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(bx + 2 * mid + 1) < zq) lo = mid + 1; else hi = mid;
+        }
+        th = lo;
+    }
+    float best = INFINITY;
+    {
+        const float zz[1] = {zq};
+        const int ta = th > 0 ? th - 1 : 0, tb = th + 1 < ntiles ? th + 1 : ntiles - 1;
+        for (int t = ta; t <= tb; t++) best = scan_tile_min<1>(gtiles + (size_t)t * STAGE_FLOATS, zz, has_w, best);
+    }
+    if (!(best < 1.0e30f)) best = ref_bias;                        // inf / NaN rows: finite reference
+    const float m = floorf(best) - ref_bias;
+    const float nm = -m;
+
+    // ---- the tiles this query can see: intervals within sqrt(m + 128) of q (conservative range, exact test below) ----
+    int ta = 1, tb = 0;                                            // empty
+    if (zq == zq) {
+        const float R = sqrtf(fmaxf(m + CULL_MARGIN, 0.f)) * 1.0001f + 1.0e-3f;
+        const float qa = zq - R, qb = zq + R;
+        int lo = 0, hi = ntiles;                                   // first tile with hi_t >= qa
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(bx + 2 * mid + 1) < qa) lo = mid + 1; else hi = mid;
+        }
+        ta = lo;
+        lo = 0; hi = ntiles;                                       // first tile with lo_t > qb
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(bx + 2 * mid) <= qb) lo = mid + 1; else hi = mid;
+        }
+        tb = lo - 1;
+        ta = ta < t0 ? t0 : ta;
+        tb = tb > t1 - 1 ? t1 - 1 : tb;
+    }
+    const int wa = __reduce_min_sync(FULL, ta <= tb ? ta : 0x7fffffff);
+    const int wb = __reduce_max_sync(FULL, ta <= tb ? tb : -1);
+
+    double S = 0.0;
+    float sum = 0.f;
+#pragma unroll 1
+    for (int t = wa; t <= wb; t++) {
+        const float4 r0 = __ldg(mom + 3 * (size_t)t);              // lo, hi, centre, radius
+        const float gap = fmaxf(fmaxf(r0.x - zq, zq - r0.y), 0.f);
+        const bool in = (t >= ta) && (t <= tb) && (r0.x <= r0.y) && !(gap * gap - m > CULL_MARGIN);
+        const float s = zq - r0.z;
+        const bool wide = in && !(fabsf(s) * r0.w <= D1_SR_MAX);
+        if (__any_sync(FULL, in && !wide)) {
+            const float4 r1 = __ldg(mom + 3 * (size_t)t + 1);      // B0..B3
+            const float4 r2 = __ldg(mom + 3 * (size_t)t + 2);      // B4, B5
+            float p = fmaf(r2.y, s, r2.x);
+            p = fmaf(p, s, r1.w);
+            p = fmaf(p, s, r1.z);
+            p = fmaf(p, s, r1.y);
+            p = fmaf(p, s, r1.x);
+            const float e = ex2_neg(fmaf(s, s, nm));
+            if (in && !wide) sum = fmaf(e, p, sum);
+        }
+        if (__any_sync(FULL, wide)) {                               // sparse tails: this tile point by point
+            const float* __restrict__ tile = gtiles + (size_t)t * STAGE_FLOATS;
+            float sd = 0.f;
+#pragma unroll 2
+            for (int j = 0; j < TN; j += 4) {
+                const float4 x = __ldg(reinterpret_cast<const float4*>(tile + j));
+                const float4 w = __ldg(reinterpret_cast<const float4*>(tile + TN + j));
+                const float d0 = zq - x.x, d1 = zq - x.y, d2 = zq - x.z, d3 = zq - x.w;
+                sd = fmaf(w.x, ex2_neg(fmaf(d0, d0, nm)), sd);
+                sd = fmaf(w.y, ex2_neg(fmaf(d1, d1, nm)), sd);
+                sd = fmaf(w.z, ex2_neg(fmaf(d2, d2, nm)), sd);
+                sd = fmaf(w.w, ex2_neg(fmaf(d3, d3, nm)), sd);
+            }
+            if (wide) sum += sd;
+        }
+        if ((t & (D1_FOLD - 1)) == D1_FOLD - 1) { S += (double)sum; sum = 0.f; }
+    }
+    S += (double)sum;
+    if (!(zq == zq)) S = NAN;
+
+    const float mref[1] = {m};
+    const double Sv[1] = {S};
+    finish_queries<1, 1, D1_NT>(L, job, qbase, tid, M, mref, Sv, s_last);
+}
+
 template <int D, int Q>
 static cudaError_t launch_score_dq(const ScoreLaunch& L, int njobs, long long max_rows, int max_split,
                                    int max_ntiles, cudaStream_t st)
 {
     constexpr int QB = pq_mode(D, Q) ? 32 : NT * Q;
     dim3 grid((unsigned)((max_rows + QB - 1) / QB), (unsigned)njobs, (unsigned)max_split);
+    if constexpr (D == 1 && Q == queries_per_thread(1)) {
+        // the culled 1-D path: sorted intervals + far-field tile records (the all-pairs instantiation, Q = 8, keeps the pair loop)
+        bool all_mom = true;
+        for (int j = 0; j < njobs; j++) all_mom = all_mom && L.jobs[j].cull;
+        if (all_mom) {
+            dim3 g1((unsigned)((max_rows + D1_NT - 1) / D1_NT), (unsigned)njobs, (unsigned)max_split);
+            skb_score_d1_kernel<<<g1, D1_NT, 0, st>>>(L);
+            count_launch();
+            return cudaGetLastError();
+        }
+    }
     if constexpr (pq_mode(D, Q)) {
         const size_t smem = pq_smem_bytes(D);
         bool stats = false;

@@ -51,6 +51,81 @@ def test_config5_top_8d_4e6_rows_weighted():
     print("d=8 N=4e6: max |dlogp| %.2e, device fit %.1f ms" % (err, fit_ms))
 
 
+@pytest.mark.parametrize("n,h,weighted", [(1000000, 0.1, True), (1000000, 0.05, False), (100000, 0.3, True)])
+def test_d1_far_field_records_at_full_size(n, h, weighted):
+    """1-D KDEs are scored from per-tile far-field records (one exponential x a degree-5 polynomial per 128-point tile,
+    skb_score_d1_kernel) instead of pair terms; the bar is the same 1e-4 against the fp64 brute force."""
+    err, fit_ms = _big_case(1, n, h, 610 + int(100 * h), weighted=weighted)
+    print("d=1 N=%d h=%g: max |dlogp| %.2e, device fit %.1f ms" % (n, h, err, fit_ms))
+
+
+def test_d1_far_field_equals_the_pair_loop_on_the_same_rounded_coordinates():
+    """The far-field path against the all-pairs fp32 kernel (culling off) on the SAME handle: both see the same fp32
+    coordinates, so the difference is the method's own error (series remainder + summation order), at a bandwidth
+    (h = 0.02: |z| c up to ~200) where the fp32 coordinates themselves cost more than that against the fp64 oracle."""
+    from skysampler_b200 import GaussianKDE, _cabi, synth
+    n, h = 400000, 0.02
+    x = synth.mixture_big(1, n, 640)
+    m1, pm, comps, std2 = synth.whiten_params(x[::7])
+    z = np.ascontiguousarray((x - m1) @ comps.T / std2)
+    w = synth.wide_weights(n, 641)
+    q = synth.queries(z, h, 20000, 642, tail_frac=0.2, tail_scale=2.0)
+    kde = GaussianKDE(h).fit(z, sample_weight=w)
+    got = kde.score_samples(q)
+    with _cabi.option("cull", 0):
+        dense = kde.score_samples(q)
+    kde.close()
+    near = dense >= dense.max() - 100.0
+    assert near.sum() > 15000
+    assert np.abs(got[near] - dense[near]).max() <= 5e-6, float(np.abs(got[near] - dense[near]).max())
+    far = ~near & np.isfinite(dense)
+    assert np.array_equal(np.isfinite(got), np.isfinite(dense))
+    if far.any():
+        assert (np.abs(got[far] - dense[far]) / np.abs(dense[far])).max() <= 1e-6
+
+
+def test_d1_far_field_on_degenerate_layouts():
+    """(Whitened data: |z| of order 10; the fp32 coordinates of every kernel resolve 2^-24 |z| / h.)
+    Ties (zero-width tiles), a lattice, huge gaps (tiles far too wide for the series -> point-by-point path), a set
+    smaller than one tile, queries on points / in gaps / far outside; weighted and unweighted."""
+    from skysampler_b200 import GaussianKDE, _cabi
+    rs = np.random.RandomState(77)
+    h = 0.05
+    sets = {
+        "ties": np.repeat(rs.normal(size=300), 40),
+        "lattice": np.arange(50000) * 1.0e-4,
+        "gaps": np.concatenate([rs.normal(size=3000) * 1e-3 + c for c in (-5.0, -1.0, 0.0, 0.7, 8.0)]),
+        "tiny": rs.normal(size=37),
+        "wide": np.clip(rs.standard_cauchy(size=20000), -20.0, 20.0),     # fp32 coordinates: |x| / h stays within a few hundred
+    }
+    for name, x in sets.items():
+        z = np.ascontiguousarray(x.reshape(-1, 1))
+        for weighted in (False, True):
+            w = 10.0 ** rs.uniform(-6, 0, size=len(z)) if weighted else None
+            q = np.concatenate([x[rs.randint(0, len(x), 300)], x[rs.randint(0, len(x), 300)] + h * rs.normal(size=300),
+                                rs.uniform(x.min() - 1, x.max() + 1, 300), [x.min() - 30 * h, x.max() + 30 * h, x.max() + 100.0]]).reshape(-1, 1)
+            kde = GaussianKDE(h).fit(z, sample_weight=w)
+            got = kde.score_samples(q)
+            again = kde.score_samples(q[100:700])
+            with _cabi.option("cull", 0):
+                dense = kde.score_samples(q)                      # the fp32 pair loop over every point, same coordinates
+            kde.close()
+            assert np.array_equal(again, got[100:700]), name
+            ref = cbrute.score(z, w, h, q)
+            fin = np.isfinite(ref)
+            assert np.array_equal(np.isfinite(got), fin), name
+            # the method's own error (series remainder, summation order): against the pair loop on the same fp32 coordinates
+            assert (np.abs(got[fin] - dense[fin]) / np.maximum(1.0, np.abs(dense[fin]))).max() <= 5e-6, (name, weighted)
+            # against the fp64 oracle: 1e-4 where the density lives; deeper rows hang on one neighbour ~10 scaled units
+            # away and carry the fp32 coordinate rounding of every kernel (2 d 2^-24 |z| c), relative 1e-5 there
+            near = fin & (ref >= ref[fin].max() - 40.0)
+            tol = TOL if np.abs(x).max() / h <= 100.0 else 3.0 * TOL     # |z| / h up to 400 here ("gaps", "wide"): fp32 coordinates
+            assert np.abs(got[near] - ref[near]).max() <= tol, (name, weighted, float(np.abs(got[near] - ref[near]).max()))
+            far = fin & ~near
+            if far.any():
+                assert (np.abs(got[far] - ref[far]) / np.abs(ref[far])).max() <= 1e-5, (name, weighted)
+
+
 def _shell(rs, n, d, r_lo, r_hi):
     v = rs.normal(size=(n, d))
     v /= np.linalg.norm(v, axis=1, keepdims=True)

@@ -1,2 +1,1 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-VARIANTS="default hs0" bash tools/ab_pq.sh 2>/dev/null | grep -v "^+"
+python -m pytest tests/test_gpu_large.py -m gpu -x -q -k "d1" 2>&1 | tail -30
