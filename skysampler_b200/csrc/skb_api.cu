@@ -718,6 +718,7 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
     SKB_CUDA_C(launch_kd_order(k->zt64, d_w, N, nv, d, hk.c, d_perm, k->dk, st));     // also fills dk->glo / ghi
     SKB_CUDA_C(launch_pack(k->zt64, d_perm, d, hk.c, d_w, 1.0 / wmax, k->tiles, hk.ntiles, k->boxes, k->sboxes, cboxes, st));
     SKB_CUDA_C(launch_moments(k->tiles, k->boxes, hk.ntiles, const_cast<float*>(hk.mom), st));
+    if (d == 2) SKB_CUDA_C(launch_moments2(k->tiles, k->boxes, hk.ntiles, st));
     SKB_CUDA_C(cudaEventRecord(ev1, st));
     SKB_CUDA_C(cudaMemcpyAsync(hk.glo, reinterpret_cast<char*>(k->dk) + offsetof(KdeDev, glo), sizeof(hk.glo) + sizeof(hk.ghi),
                                cudaMemcpyDeviceToHost, st));

@@ -148,6 +148,56 @@ __global__ void skb_moment_kernel(const float* __restrict__ tiles, const float* 
     }
 }
 
+// D == 2: far-field record of every tile, written into the free part of the tile's header row (skb_internal.h: FF2_*):
+//     B_ij = (2 ln2)^(i+j) / (i! j!) * sum_p w_p tx_p^i ty_p^j 2^-(tx_p^2 + ty_p^2),   i + j <= FF2_P,
+// about the box centre.  One warp per tile, lane l owns the coefficients l, l + 32, l + 64; fp64 sums.
+__global__ void skb_moment2_kernel(float* __restrict__ tiles, const float* __restrict__ boxes, int ntiles)
+{
+    constexpr int TN = tile_points(2);
+    const int t = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
+    const int lane = threadIdx.x & 31;
+    if (t >= ntiles) return;
+    float* tile = tiles + (size_t)t * stage_floats(2);
+    float* hdr = tile + 3 * TN;
+    const float lox = boxes[4 * t], loy = boxes[4 * t + 1], hix = boxes[4 * t + 2], hiy = boxes[4 * t + 3];
+    const bool valid = (lox <= hix) && (loy <= hiy);
+    const float cx = 0.5f * lox + 0.5f * hix, cy = 0.5f * loy + 0.5f * hiy;
+    const double L2 = 2.0 * 0.693147180559945309417232121458;
+    for (int idx = lane; idx < FF2_NCOEF; idx += 32) {
+        int i = 0, off = 0;                                   // row i starts at off = i (P + 1) - i (i - 1) / 2
+        while (off + (FF2_P + 1 - i) <= idx) { off += FF2_P + 1 - i; i++; }
+        const int j = idx - off;
+        double a = 0.0;
+        for (int o = 0; o < TN; o++) {
+            const double w = (double)tile[2 * TN + o];
+            if (!(w > 0.0)) continue;
+            const double tx = (double)tile[o] - (double)cx, ty = (double)tile[TN + o] - (double)cy;
+            double term = w * exp2(-(tx * tx + ty * ty));
+            for (int k = 0; k < i; k++) term *= tx;
+            for (int k = 0; k < j; k++) term *= ty;
+            a += term;
+        }
+        double f = 1.0;
+        for (int k = 1; k <= i; k++) f *= L2 / (double)k;
+        for (int k = 1; k <= j; k++) f *= L2 / (double)k;
+        hdr[FF2_OFF + 4 + idx] = valid ? (float)(a * f) : 0.f;
+    }
+    if (lane == 0) {
+        hdr[FF2_OFF] = valid ? cx : 0.f;
+        hdr[FF2_OFF + 1] = valid ? cy : 0.f;
+        hdr[FF2_OFF + 2] = valid ? fmaxf(hix - cx, cx - lox) * 1.000001f : -1.f;
+        hdr[FF2_OFF + 3] = valid ? fmaxf(hiy - cy, cy - loy) * 1.000001f : -1.f;
+    }
+}
+
+cudaError_t launch_moments2(float* tiles, const float* boxes, int ntiles, cudaStream_t st)
+{
+    if (ntiles <= 0) return cudaSuccess;
+    skb_moment2_kernel<<<(unsigned)((ntiles + 7) / 8), 256, 0, st>>>(tiles, boxes, ntiles);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_moments(const float* tiles, const float* boxes, int ntiles, float* mom, cudaStream_t st)
 {
     if (!mom || ntiles <= 0) return cudaSuccess;

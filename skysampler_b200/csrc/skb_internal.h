@@ -88,6 +88,14 @@ __host__ __device__ constexpr int queries_per_thread(int D)
 __host__ __device__ constexpr int queries_per_thread_dense(int D) { return (D <= 4 ? 8 : (D <= 8 ? 4 : 2)) * SKB_DENSE_QMUL; }
 __host__ __device__ constexpr int stage_floats(int D) { return (D + 2) * tile_points(D); }   // D coords, weights, header (box)
 
+// D == 2 far-field record in a tile's header row: floats [FF2_OFF, FF2_OFF + 4) = centre x, y, half widths rx, ry (rx < 0:
+// no record), then the (FF2_P + 1)(FF2_P + 2) / 2 coefficients B_ij, i + j <= FF2_P, row i = B_i0 .. B_i,P-i
+constexpr int FF2_P = 12;
+constexpr int FF2_OFF = 8;
+constexpr int FF2_NCOEF = (FF2_P + 1) * (FF2_P + 2) / 2;
+constexpr float FF2_SR_MAX = 1.7f / 1.3862943611198906f;      // z = 2 ln2 (|sx| rx + |sy| ry) <= 1.7: z^13 / 13! e^2z < 5e-6
+static_assert(FF2_OFF + 4 + FF2_NCOEF <= SKB_TN_LO, "the far-field record must fit the header row of a 2-D tile");
+
 // Device-resident description of one fitted KDE (one per handle, uploaded at skb_create).
 struct KdeDev {
     const float* tiles;      // [ntiles][D+2][tile_points(D)]
@@ -228,6 +236,7 @@ cudaError_t launch_draw(const KdeDev* kde, int D, long long M, const double* u, 
                         int rcol, double rmin, double rmax, int max_attempts,
                         long long* out_idx, double* out_x, long long ld_out, double* out_z,
                         unsigned char* out_flag, unsigned long long* n_flagged, cudaStream_t st);
+cudaError_t launch_moments2(float* tiles, const float* boxes, int ntiles, cudaStream_t st);
 cudaError_t launch_moments(const float* tiles, const float* boxes, int ntiles, float* mom, cudaStream_t st);
 cudaError_t launch_cs_index(const double* cumsum, long long N, int* index, int buckets, cudaStream_t st);
 cudaError_t launch_compact(const unsigned char* flags, long long M, const void* rows, int elem_bytes,

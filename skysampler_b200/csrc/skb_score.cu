@@ -351,6 +351,9 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
         // binades beyond the reference, every term 2^(m - acc) of the tile flushes to zero in fp32 — the
         // tile contributes exactly nothing and is skipped (warp uniform; other queries' boxes never change
         // a query's own arithmetic).
+        bool own_cull[Q];                                  // this query's own box test (the tile is visited if ANY query needs it)
+#pragma unroll
+        for (int q = 0; q < Q; q++) own_cull[q] = false;
         if (job.cull) {
             const float* hdr = tile + (D + 1) * TN;
             bool skip = true;
@@ -363,13 +366,73 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
                     const float gap = fmaxf(fmaxf(hdr[k] - zq, zq - hdr[D + k]), 0.f);
                     lb = fmaf(gap, gap, lb);
                 }
-                skip &= (lb - mref[q] > CULL_MARGIN);
+                own_cull[q] = (lb - mref[q] > CULL_MARGIN);
+                skip &= own_cull[q];
             }
             if (__all_sync(0xffffffffu, skip)) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_bar[s]);
                 n_culled++;
                 continue;
+            }
+        }
+        // ---- D == 2: far-field record of the tile (skb_fit.cu: skb_moment2_kernel; it rides in the tile's header row and
+        // arrived with the same TMA copy).  About the box centre c (s = q - c, t = x - c) a pair term is
+        //     2^-|s - t|^2 = 2^-|s|^2 * e^(2 ln2 s.t) * 2^-|t|^2,
+        // so the tile contributes 2^-|s|^2 * sum_{i+j<=12} B_ij sx^i sy^j; the Taylor series of e^u is cut after u^12 only
+        // where |u| <= 2 ln2 (|sx| rx + |sy| ry) <= 1.7: relative remainder < 5e-6 of the tile's own positive sum.  One exponential
+        // and 104 FMAs instead of 128 exponentials (the pair loop sits on the MUFU.EX2 roofline in 2-D).  Which path a
+        // (query, tile) takes depends on the query and the fitted KDE alone; a query whose own box test culls the tile
+        // takes the value 0 that the pair loop would give it; a value at the overflow limit goes to the pair loop, which
+        // re-centres.  When every query of the warp is served the pair loop is skipped.
+        bool ffq[Q];
+        float ffv[Q];
+#pragma unroll
+        for (int q = 0; q < Q; q++) { ffq[q] = false; ffv[q] = 0.f; }
+        if constexpr (D == 2 && Q == queries_per_thread(2)) {
+            if (job.cull) {
+                const float* hdr = tile + (D + 1) * TN;
+                const float4 cr = *reinterpret_cast<const float4*>(hdr + FF2_OFF);     // cx, cy, rx, ry (rx < 0: no record)
+                const float* B = hdr + FF2_OFF + 4;
+                float sx[Q], sy[Q], p[Q];
+#pragma unroll
+                for (int q = 0; q < Q; q++) { sx[q] = q2[q][0] - cr.x; sy[q] = q2[q][1] - cr.y; p[q] = 0.f; }
+#pragma unroll
+                for (int i = FF2_P; i >= 0; i--) {
+                    const int n = FF2_P + 1 - i;                                      // row i holds B_i0 .. B_i,n-1
+                    const int off = i * (FF2_P + 1) - (i * (i - 1)) / 2;
+                    float in[Q];
+#pragma unroll
+                    for (int q = 0; q < Q; q++) in[q] = B[off + n - 1];
+#pragma unroll
+                    for (int j = n - 2; j >= 0; j--) {
+                        const float b = B[off + j];
+#pragma unroll
+                        for (int q = 0; q < Q; q++) in[q] = fmaf(in[q], sy[q], b);
+                    }
+#pragma unroll
+                    for (int q = 0; q < Q; q++) p[q] = fmaf(p[q], sx[q], in[q]);
+                }
+                bool all = true;
+#pragma unroll
+                for (int q = 0; q < Q; q++) {
+                    const float v = ex2_neg(fmaf(sy[q], sy[q], fmaf(sx[q], sx[q], nm2[q]))) * p[q];
+                    const bool crit = (fabsf(sx[q]) * cr.z + fabsf(sy[q]) * cr.w <= FF2_SR_MAX) && (cr.z >= 0.f);
+                    ffq[q] = own_cull[q] || (crit && (v < OVERFLOW_LIMIT));
+                    ffv[q] = own_cull[q] ? 0.f : v;
+                    all &= ffq[q];
+                }
+                if (__all_sync(0xffffffffu, all)) {
+#pragma unroll
+                    for (int q = 0; q < Q; q++) {
+                        S[q] += (double)ffv[q];
+                        if (ffv[q] > 0.f)
+                            bmin[q] = fminf(bmin[q], mref[q] - (float)((__float_as_int(ffv[q]) >> 23) - 128));
+                        ffq[q] = false;                                               // consumed
+                    }
+                    n_blocks++;
+                    goto tile_done;
+                }
             }
         }
 #pragma unroll 1
@@ -385,7 +448,7 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
 #pragma unroll
                 for (int q = 0; q < Q; q++) {
                     float lo, hi; upk(sum2[q], lo, hi);
-                    ts[q] = lo + hi;
+                    ts[q] = ffq[q] ? 0.f : lo + hi;                  // a query served by the far-field record ignores the pair loop
                     bad |= !(ts[q] < OVERFLOW_LIMIT);
                 }
                 if (!__any_sync(0xffffffffu, bad)) {
@@ -429,6 +492,13 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
                 }
             }
         }
+#pragma unroll
+        for (int q = 0; q < Q; q++)
+            if (ffq[q]) {
+                S[q] += (double)ffv[q];
+                if (ffv[q] > 0.f) bmin[q] = fminf(bmin[q], mref[q] - (float)((__float_as_int(ffv[q]) >> 23) - 128));
+            }
+    tile_done:
         // move the reference down when the sums have shown a closer point than it was built for (exact:
         // S is rescaled by a power of two); a tighter reference culls more of the tiles still to come
 #pragma unroll

@@ -84,6 +84,34 @@ def test_d1_far_field_equals_the_pair_loop_on_the_same_rounded_coordinates():
         assert (np.abs(got[far] - dense[far]) / np.abs(dense[far])).max() <= 1e-6
 
 
+@pytest.mark.parametrize("n,h", [(1000000, 0.1), (100000, 0.1), (300000, 0.03)])
+def test_d2_far_field_records_against_oracle_and_pair_loop(n, h):
+    """2-D: a tile's 128 pair terms are replaced by its far-field record (one exponential x a degree-10 bivariate
+    polynomial, skb_score_kernel<2,2>) wherever the series' remainder bound allows.  Bar against the fp64 brute force:
+    1e-4; against the fp32 pair loop over every point on the same handle (culling off): the method's own error."""
+    from skysampler_b200 import GaussianKDE, _cabi, synth
+    x = synth.mixture_big(2, n, 650)
+    w = synth.wide_weights(n, 651)
+    m1, pm, comps, std2 = synth.whiten_params(x[::7], w[::7])
+    z = np.ascontiguousarray((x - m1) @ comps.T / std2)
+    q = synth.queries(z, h, 4000, 652, tail_frac=0.15, tail_scale=2.0)
+    kde = GaussianKDE(h).fit(z, sample_weight=w)
+    got = kde.score_samples(q)
+    again = kde.score_samples(q[1000:3000])
+    with _cabi.option("cull", 0):
+        dense = kde.score_samples(q)
+    kde.close()
+    assert np.array_equal(again, got[1000:3000])
+    ref = cbrute.score(z, w, h, q)
+    near = ref >= ref.max() - 100.0
+    assert near.sum() >= 3000
+    assert np.abs(got[near] - ref[near]).max() <= TOL, float(np.abs(got[near] - ref[near]).max())
+    assert np.abs(got[near] - dense[near]).max() <= 1e-5, float(np.abs(got[near] - dense[near]).max())
+    far = ~near & np.isfinite(ref)
+    if far.any():
+        assert np.all(np.isfinite(got[far])) and (np.abs(got[far] - ref[far]) / np.abs(ref[far])).max() <= 1e-5
+
+
 def test_d1_far_field_on_degenerate_layouts():
     """(Whitened data: |z| of order 10; the fp32 coordinates of every kernel resolve 2^-24 |z| / h.)
     Ties (zero-width tiles), a lattice, huge gaps (tiles far too wide for the series -> point-by-point path), a set

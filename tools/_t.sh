@@ -1,1 +1,2 @@
-python -m pytest tests/test_gpu_large.py -m gpu -x -q -k "d1" 2>&1 | tail -30
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python tools/perf_scan.py 1,2,3,4 1000000 2>&1 | grep -v Warn
