@@ -27,7 +27,10 @@ typedef unsigned long long u64;
 #endif
 // training points per tile (= kd leaf size).  Smaller leaves have tighter boxes and cull more, which pays
 // in higher dimensions (measured d=8 +6 %, d=16 +14 % for 64 vs 128); below d=5 128 is as good or better.
-__host__ __device__ constexpr int tile_points(int D) { return D <= 4 ? SKB_TN_LO : (D <= 8 ? SKB_TN_MID : SKB_TN_HI); }
+#ifndef SKB_TN_34
+#define SKB_TN_34 128
+#endif
+__host__ __device__ constexpr int tile_points(int D) { return D <= 2 ? SKB_TN_LO : (D <= 4 ? SKB_TN_34 : (D <= 8 ? SKB_TN_MID : SKB_TN_HI)); }
 #ifndef SKB_NSTAGE
 #define SKB_NSTAGE 3
 #endif
