@@ -112,6 +112,33 @@ def test_d2_far_field_records_against_oracle_and_pair_loop(n, h):
         assert np.all(np.isfinite(got[far])) and (np.abs(got[far] - ref[far]) / np.abs(ref[far])).max() <= 1e-5
 
 
+@pytest.mark.parametrize("d", [1, 2])
+def test_far_field_paths_under_training_splits_and_partial_states(d):
+    """Training-set splits (blockIdx.z: tile ranges) and the partial (m, s) outputs that the multi-GPU combine consumes go
+    through the far-field kernels too: forced splits agree with the unsplit launch, the partial state reproduces log p."""
+    from skysampler_b200 import GaussianKDE, _cabi, synth
+    n, h = 300000, 0.1
+    x = synth.mixture_big(d, n, 660 + d)
+    w = synth.wide_weights(n, 670 + d)
+    m1, pm, comps, std2 = synth.whiten_params(x[::7], w[::7])
+    z = np.ascontiguousarray((x - m1) @ comps.T / std2)
+    q = synth.queries(z, h, 3000, 680 + d, tail_frac=0.1, tail_scale=2.0)
+    kde = GaussianKDE(h).fit(z, sample_weight=w)
+    one = kde.score_samples(q)
+    with _cabi.option("force_nsplit", 5):
+        five = kde.score_samples(q)
+    mm, ss = kde.score_partial(q)
+    kde.close()
+    near = one >= one.max() - 100.0
+    assert np.abs(one - five)[near].max() <= 2e-5
+    ref = cbrute.score(z, w, h, q[:500])
+    assert np.abs(five[:500] - ref)[near[:500]].max() <= TOL
+    # partial state: log p = log_knorm - log(sum w) + m + log(s)
+    lk = -0.5 * d * np.log(2 * np.pi) - d * np.log(h)
+    lp = lk - np.log(w.sum()) + mm + np.log(ss)
+    assert np.abs(lp - one)[near].max() <= 1e-9
+
+
 def test_d1_far_field_on_degenerate_layouts():
     """(Whitened data: |z| of order 10; the fp32 coordinates of every kernel resolve 2^-24 |z| / h.)
     Ties (zero-width tiles), a lattice, huge gaps (tiles far too wide for the series -> point-by-point path), a set
