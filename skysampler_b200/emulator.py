@@ -263,15 +263,19 @@ class KFoldCV(object):
         self.reference_bug_compat = reference_bug_compat
 
     def _loop_bandwidths(self, bandwidths):
+        """emulator.py:422-426.  The folds do not depend on the bandwidth (no random numbers are drawn in the loops), so a
+        sweep splits and re-whitens each fold ONCE and only re-fits the device KDE per bandwidth (a few ms: the fit is a
+        device kd ordering) — the reference re-slices the DataFrames and rebuilds its tree for every (bandwidth, fold)."""
+        folds = [self._split(ifold) for ifold in np.arange(self.nfold)]
         scores = []
         for bw in bandwidths:
-            scores.append(self._loop_cv(bw))
+            scores.append(self._loop_cv(bw, folds=folds))
         return scores
 
-    def _loop_cv(self, bandwidth):
+    def _loop_cv(self, bandwidth, folds=None):
         mscores = []
         for ifold in np.arange(self.nfold):
-            train, test = self._split(ifold)
+            train, test = folds[ifold] if folds is not None else self._split(ifold)
             iarr = np.arange(len(test.data))
             iparts = partition(iarr, self.nprocess)
             if self.reference_bug_compat:
