@@ -35,7 +35,7 @@ def weighted_std(values, weights):
     return np.sqrt(variance)
 
 
-def _as_matrix(x, allow_torch=True):
+def _as_matrix(x, allow_torch=True, check_finite=True):
     """DataFrame / ndarray / torch tensor -> C-contiguous 2-D float matrix (float64 unless float32 given)."""
     if allow_torch and _cabi._is_torch(x):
         if x.dim() == 1:
@@ -52,9 +52,14 @@ def _as_matrix(x, allow_torch=True):
         raise ValueError("Expected 2D array, got %dD array instead" % x.ndim)
     if x.dtype != np.float32:
         x = x.astype(np.float64, copy=False)
-    if not np.isfinite(x).all():
-        # sklearn's validate_data raises the same way (KernelDensity.fit / score_samples, _kde.py:233,272)
-        raise ValueError("Input X contains NaN or infinity.")
+    if check_finite:
+        # sklearn's validate_data raises the same way (KernelDensity.fit / score_samples, _kde.py:233,272) and uses the same
+        # shortcut (utils/validation.py: _assert_all_finite): one pass for the sum, the element-wise test only if that
+        # sum is not finite (an overflowing sum of finite values is rare and merely costs the slow path)
+        with np.errstate(over="ignore", invalid="ignore"):
+            total = x.sum(dtype=np.float64)
+        if not np.isfinite(total) and not np.isfinite(x).all():
+            raise ValueError("Input X contains NaN or infinity.")
     return np.ascontiguousarray(x)
 
 
@@ -123,10 +128,10 @@ class GaussianKDE(object):
         return self._h
 
     # -- scoring ----------------------------------------------------------------------------------
-    def score_samples(self, X, cols=None, is_whitened=True, out=None, stream=None):
+    def score_samples(self, X, cols=None, is_whitened=True, out=None, stream=None, _validated=False):
         """log p(X): float64 ndarray for host input, torch CUDA tensor for CUDA input (zero copy)."""
         h = self._handle()
-        X = _as_matrix(X)
+        X = _as_matrix(X, check_finite=not _validated)
         m, ld = X.shape
         if cols is None and ld != self.ndim_:
             raise ValueError("X has %d features, but GaussianKDE is expecting %d features as input." % (ld, self.ndim_))
@@ -432,7 +437,7 @@ class KDEContainer(object):
         if X.shape[1] != self.ndim:
             raise ValueError("X has %d features, but KDEContainer is expecting %d features as input."
                              % (X.shape[1], self.ndim))
-        res = self.kde.score_samples(X, is_whitened=False)
+        res = self.kde.score_samples(X, is_whitened=False, _validated=True)      # X went through _as_matrix above
         return res, self._jacobian_det
 
     def drop_kde(self):

@@ -201,3 +201,22 @@ def test_feature_tables_match_reference():
     np.testing.assert_allclose(fsc2.features.values.astype(float), g["wide_features"], rtol=0, atol=0)
     wc = features.construct_wide_container(info, wide_settings, nbins=10, nmax=150, seed=4)
     assert len(wc["container"].data) == 1500 and wc["container"].ndim == 2
+
+
+def test_query_validation_matches_sklearn_and_takes_the_one_pass_shortcut():
+    """`KernelDensity.score_samples` rejects NaN / inf rows with a ValueError (validate_data, sklearn _kde.py:272); the
+    host mirror does the same with sklearn's own shortcut (sum first, element-wise only if the sum is not finite)."""
+    from skysampler_b200.kde import _as_matrix
+    rs = np.random.RandomState(3)
+    x = rs.normal(size=(1000, 3))
+    assert _as_matrix(x) is x or np.array_equal(_as_matrix(x), x)
+    for bad in (np.nan, np.inf, -np.inf):
+        y = x.copy(); y[517, 1] = bad
+        with pytest.raises(ValueError, match="NaN or infinity"):
+            _as_matrix(y)
+        assert np.array_equal(_as_matrix(y, check_finite=False), y, equal_nan=True)
+    big = np.full((4, 2), 1.0e308)                      # finite values whose sum overflows: slow path, still accepted
+    assert np.array_equal(_as_matrix(big), big)
+    f = x.astype(np.float32)
+    assert _as_matrix(f).dtype == np.float32
+    assert _as_matrix(np.asfortranarray(x)).flags["C_CONTIGUOUS"]
