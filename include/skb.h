@@ -231,6 +231,11 @@ int skb_measure_pipes(int device, double ms_each, double* fma_lane_per_s, double
  *                   The initial value is 0 when SKB_NO_CULL=1 is in the environment at load time.
  *   "force_nsplit"  > 0: split the training tiles over that many CTAs per query block (experiments).
  *   "stats"         1: launches made while it is set count evaluated pairs / culled tiles (skb_debug_counters).
+ *   "kernel"        0 (default): route by dimension (d = 1 sorted intervals + far-field records, d = 2 lanes = queries with
+ *                   far-field records, d = 3..5 sorted-incidence pipeline, d >= 6 per-query kernel); 1 / 2 force the
+ *                   single-launch kernels / the pipeline (A/B runs).
+ *   "host_stage_rows" > 0: rows per staged chunk of a host-buffer call (default 0: one chunk up to 2^21 rows — measured
+ *                   faster than overlapping two half uploads — and chunks of 2^19 beyond).
  */
 int skb_set_option(const char* name, int value);
 int skb_get_option(const char* name);               /* -1 for an unknown name */

@@ -455,6 +455,15 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
 // rows per chunk of a device-resident table (bounds the per-call scratch) and of a host table (copy / compute overlap)
 static const long long STAGE_ROWS = 1LL << 22;
 static const long long HOST_STAGE_ROWS = 1LL << 19;
+static std::atomic<long long> g_opt_host_rows{0};       // diagnostic: rows per staged chunk of host-buffer calls (0: the policy below)
+// Host-buffer calls: up to 2^21 rows go as ONE chunk (one ordering pass, one launch set), longer tables in chunks of 2^19 with
+// the upload of chunk i+1 overlapping the kernels of chunk i.
+static long long host_stage_step(long long M)
+{
+    const long long g = g_opt_host_rows.load(std::memory_order_relaxed);
+    if (g > 0) return M > g ? g : M;
+    return M > (1 << 21) ? HOST_STAGE_ROWS : M;
+}
 
 // Copy / compute overlap for calls whose buffers live in host memory: uploads and downloads run on a private
 // copy stream, ordered against the caller's stream with events (two buffers in flight).
@@ -790,7 +799,7 @@ static int score_one(skb_handle h, const void* q, int q_dtype, int64_t M, int64_
     // staged path: chunks of rows through device scratch, double buffered — the upload of chunk i+1 (copy stream)
     // overlaps the kernels of chunk i, and the download of chunk i is issued after the kernels of chunk i+1 are
     // queued, so that a blocking (pageable) download never leaves the GPU without work
-    const int64_t step = M > (1 << 21) ? HOST_STAGE_ROWS : M;       // up to 2^21 rows: one chunk (one ordering pass, one launch set)
+    const int64_t step = host_stage_step(M);
     const int64_t nchunks = (M + step - 1) / step;
     void* qbuf[2] = {nullptr, nullptr};
     double* obuf[2] = {nullptr, nullptr};
@@ -947,7 +956,7 @@ int skb_ratio_accept(const skb_handle* kdes, int n_kde, const int32_t* sign, con
         return SKB_OK;
     }
     // host buffers: chunks through device scratch with the copies on a side stream (see score_one)
-    const int64_t step = M > (1 << 21) ? HOST_STAGE_ROWS : M;       // up to 2^21 rows: one chunk (one ordering pass, one launch set)
+    const int64_t step = host_stage_step(M);
     const int64_t nchunks = (M + step - 1) / step;
     const int nbuf = nchunks > 1 ? 2 : 1;
     void* qbuf[2] = {nullptr, nullptr};
@@ -1178,6 +1187,7 @@ int skb_set_option(const char* name, int value)
     if (!strcmp(name, "force_nsplit")) { g_opt_nsplit.store(value > 0 ? value : 0); return SKB_OK; }
     if (!strcmp(name, "stats")) { g_opt_stats.store(value ? 1 : 0); return SKB_OK; }
     if (!strcmp(name, "kernel")) { g_opt_kernel.store(value); return SKB_OK; }
+    if (!strcmp(name, "host_stage_rows")) { g_opt_host_rows.store(value > 0 ? value : 0); return SKB_OK; }
     return fail(SKB_EINVAL, "unknown option '%s' (cull, force_nsplit, stats)", name);
 }
 
@@ -1188,6 +1198,7 @@ int skb_get_option(const char* name)
     if (!strcmp(name, "force_nsplit")) return g_opt_nsplit.load();
     if (!strcmp(name, "stats")) return g_opt_stats.load();
     if (!strcmp(name, "kernel")) return g_opt_kernel.load();
+    if (!strcmp(name, "host_stage_rows")) return (int)g_opt_host_rows.load();
     return -1;
 }
 
