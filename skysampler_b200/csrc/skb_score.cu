@@ -397,21 +397,37 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
                 float sx[Q], sy[Q], p[Q];
 #pragma unroll
                 for (int q = 0; q < Q; q++) { sx[q] = q2[q][0] - cr.x; sy[q] = q2[q][1] - cr.y; p[q] = 0.f; }
+                if constexpr (Q == 2) {
+                    // the thread's two queries ride in one packed fp32x2 Horner chain (the coefficient is the broadcast operand)
+                    const u64 sx2 = pk(sx[0], sx[1]), sy2 = pk(sy[0], sy[1]);
+                    u64 p2 = pk(0.f, 0.f);
 #pragma unroll
-                for (int i = FF2_P; i >= 0; i--) {
-                    const int n = FF2_P + 1 - i;                                      // row i holds B_i0 .. B_i,n-1
-                    const int off = i * (FF2_P + 1) - (i * (i - 1)) / 2;
-                    float in[Q];
+                    for (int i = FF2_P; i >= 0; i--) {
+                        const int n = FF2_P + 1 - i;                                  // row i holds B_i0 .. B_i,n-1
+                        const int off = i * (FF2_P + 1) - (i * (i - 1)) / 2;
+                        u64 in2 = pk(B[off + n - 1], B[off + n - 1]);
 #pragma unroll
-                    for (int q = 0; q < Q; q++) in[q] = B[off + n - 1];
-#pragma unroll
-                    for (int j = n - 2; j >= 0; j--) {
-                        const float b = B[off + j];
-#pragma unroll
-                        for (int q = 0; q < Q; q++) in[q] = fmaf(in[q], sy[q], b);
+                        for (int j = n - 2; j >= 0; j--) in2 = fma2(in2, sy2, pk(B[off + j], B[off + j]));
+                        p2 = fma2(p2, sx2, in2);
                     }
+                    upk(p2, p[0], p[1]);
+                } else {
 #pragma unroll
-                    for (int q = 0; q < Q; q++) p[q] = fmaf(p[q], sx[q], in[q]);
+                    for (int i = FF2_P; i >= 0; i--) {
+                        const int n = FF2_P + 1 - i;
+                        const int off = i * (FF2_P + 1) - (i * (i - 1)) / 2;
+                        float in[Q];
+#pragma unroll
+                        for (int q = 0; q < Q; q++) in[q] = B[off + n - 1];
+#pragma unroll
+                        for (int j = n - 2; j >= 0; j--) {
+                            const float b = B[off + j];
+#pragma unroll
+                            for (int q = 0; q < Q; q++) in[q] = fmaf(in[q], sy[q], b);
+                        }
+#pragma unroll
+                        for (int q = 0; q < Q; q++) p[q] = fmaf(p[q], sx[q], in[q]);
+                    }
                 }
                 bool all = true;
 #pragma unroll
