@@ -234,6 +234,7 @@ int skb_measure_pipes(int device, double ms_each, double* fma_lane_per_s, double
  *   "kernel"        0 (default): route by dimension (d = 1 sorted intervals + far-field records, d = 2 lanes = queries with
  *                   far-field records, d = 3..5 sorted-incidence pipeline, d >= 6 per-query kernel); 1 / 2 force the
  *                   single-launch kernels / the pipeline (A/B runs).
+ *   "ff2_cells"     -1 (default): the 2-D second-level far-field records are used per the fitted KDE; 0 / 1 force them off / on.
  *   "host_stage_rows" > 0: rows per staged chunk of a host-buffer call (default 0: one chunk up to 2^21 rows — measured
  *                   faster than overlapping two half uploads — and chunks of 2^19 beyond).
  */

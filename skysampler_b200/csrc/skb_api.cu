@@ -89,6 +89,7 @@ static int env_int(const char* name, int dflt)
 static std::atomic<int> g_opt_cull{env_int("SKB_NO_CULL", 0) ? 0 : 1};
 static std::atomic<int> g_opt_nsplit{env_int("SKB_FORCE_NSPLIT", 0)};
 static std::atomic<int> g_opt_stats{0};
+static std::atomic<int> g_opt_ff2_cells{-1};             // diagnostic: D == 2 cell records -1 auto / 0 off / 1 on
 static std::atomic<int> g_opt_kernel{env_int("SKB_KERNEL", 0)};     // 0: work-item-per-lane kernel; 1: round-1 culled kernels (A/B runs)
 static unsigned long long* g_stats_dev[64] = {nullptr};
 
@@ -368,6 +369,7 @@ static int run_jobs_device(const DevJob* jobs, int n, bool grouped, const GroupS
             sj.nsplit = nsplit[j];
             sj.fin_slot = j;
             sj.cull = cull ? 1 : 0;
+            sj.ff2_cells = g_opt_ff2_cells.load(std::memory_order_relaxed);
             sj.perm = perm_of[j];
             sj.stats = stats;
             bool ident = true;
@@ -682,6 +684,7 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
         const size_t o_boxes = carve((size_t)hk.ntiles * 2 * d * sizeof(float));
         const size_t o_sb = carve((size_t)(hk.nsuper + hk.nchunk) * 2 * d * sizeof(float));   // super-boxes, then chunk boxes
         const size_t o_mom = carve(d == 1 ? (size_t)hk.ntiles * 12 * sizeof(float) : 0);
+        const size_t o_ff2c = carve(d == 2 ? (size_t)hk.ntiles * 4 * FF2_CELL * sizeof(float) : 0);
         const size_t o_dk = carve(sizeof(KdeDev));
         SKB_CUDA_C(cudaMalloc(&k->slab, off));
         char* base = reinterpret_cast<char*>(k->slab);
@@ -693,6 +696,7 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
         k->sboxes = reinterpret_cast<float*>(base + o_sb);
         k->dk = reinterpret_cast<KdeDev*>(base + o_dk);
         hk.mom = d == 1 ? reinterpret_cast<float*>(base + o_mom) : nullptr;
+        hk.ff2c = d == 2 ? reinterpret_cast<float*>(base + o_ff2c) : nullptr;
     }
     if (w) {
         SKB_CUDA_C(cudaMemcpyAsync(k->cumsum, cs.data(), (size_t)N * 8, cudaMemcpyHostToDevice, st));
@@ -727,7 +731,7 @@ int skb_create(const void* train, int train_dtype, int64_t N, int d, int64_t ld_
     SKB_CUDA_C(launch_kd_order(k->zt64, d_w, N, nv, d, hk.c, d_perm, k->dk, st));     // also fills dk->glo / ghi
     SKB_CUDA_C(launch_pack(k->zt64, d_perm, d, hk.c, d_w, 1.0 / wmax, k->tiles, hk.ntiles, k->boxes, k->sboxes, cboxes, st));
     SKB_CUDA_C(launch_moments(k->tiles, k->boxes, hk.ntiles, const_cast<float*>(hk.mom), st));
-    if (d == 2) SKB_CUDA_C(launch_moments2(k->tiles, k->boxes, hk.ntiles, st));
+    if (d == 2) SKB_CUDA_C(launch_moments2(k->tiles, k->boxes, hk.ntiles, const_cast<float*>(hk.ff2c), k->dk, st));
     SKB_CUDA_C(cudaEventRecord(ev1, st));
     SKB_CUDA_C(cudaMemcpyAsync(hk.glo, reinterpret_cast<char*>(k->dk) + offsetof(KdeDev, glo), sizeof(hk.glo) + sizeof(hk.ghi),
                                cudaMemcpyDeviceToHost, st));
@@ -1188,6 +1192,7 @@ int skb_set_option(const char* name, int value)
     if (!strcmp(name, "stats")) { g_opt_stats.store(value ? 1 : 0); return SKB_OK; }
     if (!strcmp(name, "kernel")) { g_opt_kernel.store(value); return SKB_OK; }
     if (!strcmp(name, "host_stage_rows")) { g_opt_host_rows.store(value > 0 ? value : 0); return SKB_OK; }
+    if (!strcmp(name, "ff2_cells")) { g_opt_ff2_cells.store(value < 0 ? -1 : (value ? 1 : 0)); return SKB_OK; }
     return fail(SKB_EINVAL, "unknown option '%s' (cull, force_nsplit, stats)", name);
 }
 
@@ -1199,6 +1204,7 @@ int skb_get_option(const char* name)
     if (!strcmp(name, "stats")) return g_opt_stats.load();
     if (!strcmp(name, "kernel")) return g_opt_kernel.load();
     if (!strcmp(name, "host_stage_rows")) return (int)g_opt_host_rows.load();
+    if (!strcmp(name, "ff2_cells")) return g_opt_ff2_cells.load();
     return -1;
 }
 

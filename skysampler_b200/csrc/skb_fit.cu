@@ -148,20 +148,28 @@ __global__ void skb_moment_kernel(const float* __restrict__ tiles, const float* 
     }
 }
 
-// D == 2: far-field record of every tile, written into the free part of the tile's header row (skb_internal.h: FF2_*):
+// D == 2: far-field records (skb_internal.h: FF2_*).  Per tile, about the box centre:
 //     B_ij = (2 ln2)^(i+j) / (i! j!) * sum_p w_p tx_p^i ty_p^j 2^-(tx_p^2 + ty_p^2),   i + j <= FF2_P,
-// about the box centre.  One warp per tile, lane l owns the coefficients l, l + 32, l + 64; fp64 sums.
-__global__ void skb_moment2_kernel(float* __restrict__ tiles, const float* __restrict__ boxes, int ntiles)
+// written into the free part of the tile's header row; and the same for each of the tile's four CELLS — the leaf split at
+// the median of its wider coordinate, each half at the median of the other coordinate (~32 points, half the radius) — into
+// the side table `cells` [tile][4][FF2_CELL].  Cells are sets of points, not ranges: the pair loop does not care about the
+// order inside a tile, so nothing is re-ordered.  One warp per tile, lane l owns the coefficients l, l + 32, l + 64; fp64 sums.
+__device__ void ff2_record(const float* sx, const float* sy, const float* sw, const unsigned char* cid, int want, int lane,
+                           float* __restrict__ out /* cx, cy, rx, ry, B[] */)
 {
     constexpr int TN = tile_points(2);
-    const int t = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
-    const int lane = threadIdx.x & 31;
-    if (t >= ntiles) return;
-    float* tile = tiles + (size_t)t * stage_floats(2);
-    float* hdr = tile + 3 * TN;
-    const float lox = boxes[4 * t], loy = boxes[4 * t + 1], hix = boxes[4 * t + 2], hiy = boxes[4 * t + 3];
+    float lox = INFINITY, loy = INFINITY, hix = -INFINITY, hiy = -INFINITY;
+    for (int o = lane; o < TN; o += 32)
+        if (sw[o] > 0.f && (want < 0 || cid[o] == want)) {
+            lox = fminf(lox, sx[o]); hix = fmaxf(hix, sx[o]);
+            loy = fminf(loy, sy[o]); hiy = fmaxf(hiy, sy[o]);
+        }
+    for (int s = 16; s > 0; s >>= 1) {
+        lox = fminf(lox, __shfl_xor_sync(0xffffffffu, lox, s)); hix = fmaxf(hix, __shfl_xor_sync(0xffffffffu, hix, s));
+        loy = fminf(loy, __shfl_xor_sync(0xffffffffu, loy, s)); hiy = fmaxf(hiy, __shfl_xor_sync(0xffffffffu, hiy, s));
+    }
     const bool valid = (lox <= hix) && (loy <= hiy);
-    const float cx = 0.5f * lox + 0.5f * hix, cy = 0.5f * loy + 0.5f * hiy;
+    const float cx = valid ? 0.5f * lox + 0.5f * hix : 0.f, cy = valid ? 0.5f * loy + 0.5f * hiy : 0.f;
     const double L2 = 2.0 * 0.693147180559945309417232121458;
     for (int idx = lane; idx < FF2_NCOEF; idx += 32) {
         int i = 0, off = 0;                                   // row i starts at off = i (P + 1) - i (i - 1) / 2
@@ -169,9 +177,9 @@ __global__ void skb_moment2_kernel(float* __restrict__ tiles, const float* __res
         const int j = idx - off;
         double a = 0.0;
         for (int o = 0; o < TN; o++) {
-            const double w = (double)tile[2 * TN + o];
-            if (!(w > 0.0)) continue;
-            const double tx = (double)tile[o] - (double)cx, ty = (double)tile[TN + o] - (double)cy;
+            const double w = (double)sw[o];
+            if (!(w > 0.0) || !(want < 0 || cid[o] == want)) continue;
+            const double tx = (double)sx[o] - (double)cx, ty = (double)sy[o] - (double)cy;
             double term = w * exp2(-(tx * tx + ty * ty));
             for (int k = 0; k < i; k++) term *= tx;
             for (int k = 0; k < j; k++) term *= ty;
@@ -180,21 +188,94 @@ __global__ void skb_moment2_kernel(float* __restrict__ tiles, const float* __res
         double f = 1.0;
         for (int k = 1; k <= i; k++) f *= L2 / (double)k;
         for (int k = 1; k <= j; k++) f *= L2 / (double)k;
-        hdr[FF2_OFF + 4 + idx] = valid ? (float)(a * f) : 0.f;
+        out[4 + idx] = valid ? (float)(a * f) : 0.f;
     }
     if (lane == 0) {
-        hdr[FF2_OFF] = valid ? cx : 0.f;
-        hdr[FF2_OFF + 1] = valid ? cy : 0.f;
-        hdr[FF2_OFF + 2] = valid ? fmaxf(hix - cx, cx - lox) * 1.000001f : -1.f;
-        hdr[FF2_OFF + 3] = valid ? fmaxf(hiy - cy, cy - loy) * 1.000001f : -1.f;
+        out[0] = cx;
+        out[1] = cy;
+        out[2] = valid ? fmaxf(hix - cx, cx - lox) * 1.000001f : -1.f;
+        out[3] = valid ? fmaxf(hiy - cy, cy - loy) * 1.000001f : -1.f;
     }
 }
 
-cudaError_t launch_moments2(float* tiles, const float* boxes, int ntiles, cudaStream_t st)
+__global__ void __launch_bounds__(256) skb_moment2_kernel(float* __restrict__ tiles, const float* __restrict__ boxes, int ntiles,
+                                                          float* __restrict__ cells)
+{
+    constexpr int TN = tile_points(2);
+    __shared__ float s_x[8][TN], s_y[8][TN], s_w[8][TN];
+    __shared__ unsigned char s_c[8][TN];
+    const int wid = threadIdx.x / 32;
+    const int t = blockIdx.x * 8 + wid;
+    const int lane = threadIdx.x & 31;
+    if (t >= ntiles) return;
+    float* tile = tiles + (size_t)t * stage_floats(2);
+    float* sx = s_x[wid]; float* sy = s_y[wid]; float* sw = s_w[wid];
+    unsigned char* cid = s_c[wid];
+    for (int o = lane; o < TN; o += 32) { sx[o] = tile[o]; sy[o] = tile[TN + o]; sw[o] = tile[2 * TN + o]; cid[o] = 255; }
+    __syncwarp();
+    ff2_record(sx, sy, sw, cid, -1, lane, tile + 3 * TN + FF2_OFF);          // the tile's own record, in its header row
+    if (!cells) return;
+    // cells: median split along the wider box coordinate, then each half along the other one (ranks by counting)
+    const bool xfirst = (boxes[4 * t + 2] - boxes[4 * t]) >= (boxes[4 * t + 3] - boxes[4 * t + 1]);
+    const float* pa = xfirst ? sx : sy;
+    const float* pb = xfirst ? sy : sx;
+    int nv = 0;
+    for (int o = 0; o < TN; o++) nv += (sw[o] > 0.f);
+    for (int o = lane; o < TN; o += 32) {
+        if (!(sw[o] > 0.f)) continue;
+        int r = 0;
+        for (int k = 0; k < TN; k++) r += (sw[k] > 0.f) && (pa[k] < pa[o] || (pa[k] == pa[o] && k < o));
+        cid[o] = (unsigned char)(r >= (nv + 1) / 2 ? 2 : 0);
+    }
+    __syncwarp();
+    int nh[2] = {0, 0};
+    for (int o = 0; o < TN; o++) if (cid[o] != 255) nh[cid[o] >> 1]++;
+    unsigned char quarter[TN / 32];
+    for (int o = lane, u = 0; o < TN; o += 32, u++) {
+        quarter[u] = 255;
+        if (cid[o] == 255) continue;
+        const int h = cid[o] >> 1;
+        int r = 0;
+        for (int k = 0; k < TN; k++) r += (cid[k] != 255) && ((cid[k] >> 1) == h) && (pb[k] < pb[o] || (pb[k] == pb[o] && k < o));
+        quarter[u] = (unsigned char)(2 * h + (r >= (nh[h] + 1) / 2 ? 1 : 0));
+    }
+    __syncwarp();
+    for (int o = lane, u = 0; o < TN; o += 32, u++) cid[o] = quarter[u];
+    __syncwarp();
+    for (int c = 0; c < 4; c++) {
+        float* rec = cells + ((size_t)t * 4 + c) * FF2_CELL;
+        ff2_record(sx, sy, sw, cid, c, lane, rec);
+        if (lane == 0) rec[FF2_CELL - 1] = 0.f;
+    }
+}
+
+// mean leaf radius rx + ry (prescaled units) over the tiles that hold points -> KdeDev::ff2_cells_on
+__global__ void __launch_bounds__(256) skb_ff2_decide_kernel(const float* __restrict__ tiles, int ntiles, KdeDev* __restrict__ kde)
+{
+    constexpr int TN = tile_points(2);
+    __shared__ double s_sum[256];
+    __shared__ int s_cnt[256];
+    double sum = 0.0;
+    int cnt = 0;
+    for (int t = threadIdx.x; t < ntiles; t += 256) {
+        const float* hdr = tiles + (size_t)t * stage_floats(2) + 3 * TN + FF2_OFF;
+        if (hdr[2] >= 0.f) { sum += (double)hdr[2] + (double)hdr[3]; cnt++; }
+    }
+    s_sum[threadIdx.x] = sum; s_cnt[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) { s_sum[threadIdx.x] += s_sum[threadIdx.x + s]; s_cnt[threadIdx.x] += s_cnt[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) kde->ff2_cells_on = (s_cnt[0] > 0 && s_sum[0] / s_cnt[0] <= (double)FF2_CELLS_MAX_R) ? 1 : 0;
+}
+
+cudaError_t launch_moments2(float* tiles, const float* boxes, int ntiles, float* cells, KdeDev* kde_dev, cudaStream_t st)
 {
     if (ntiles <= 0) return cudaSuccess;
-    skb_moment2_kernel<<<(unsigned)((ntiles + 7) / 8), 256, 0, st>>>(tiles, boxes, ntiles);
-    count_launch();
+    skb_moment2_kernel<<<(unsigned)((ntiles + 7) / 8), 256, 0, st>>>(tiles, boxes, ntiles, cells);
+    skb_ff2_decide_kernel<<<1, 256, 0, st>>>(tiles, ntiles, kde_dev);
+    count_launch(2);
     return cudaGetLastError();
 }
 

@@ -96,7 +96,10 @@ __host__ __device__ constexpr int stage_floats(int D) { return (D + 2) * tile_po
 constexpr int FF2_P = 12;
 constexpr int FF2_OFF = 8;
 constexpr int FF2_NCOEF = (FF2_P + 1) * (FF2_P + 2) / 2;
+constexpr int FF2_CELL = 96;                                  // floats per cell record in KdeDev::ff2c: cx, cy, rx, ry, B[91], pad
+constexpr float FF2_CELLS_MAX_R = 2.0f;                        // measured: never slower from 5e4 rows up (r ~ 1.1); beyond this even a cell is wider than the kernel
 constexpr float FF2_SR_MAX = 1.7f / 1.3862943611198906f;      // z = 2 ln2 (|sx| rx + |sy| ry) <= 1.7: z^13 / 13! e^2z < 5e-6
+static_assert(4 + FF2_NCOEF <= FF2_CELL && (4 * FF2_CELL) % 128 == 0, "cell record layout");
 static_assert(FF2_OFF + 4 + FF2_NCOEF <= SKB_TN_LO, "the far-field record must fit the header row of a 2-D tile");
 
 // Device-resident description of one fitted KDE (one per handle, uploaded at skb_create).
@@ -104,6 +107,8 @@ struct KdeDev {
     const float* tiles;      // [ntiles][D+2][tile_points(D)]
     const double* zt64;      // [N][D] whitened fp64 rows (draw centres)
     const double* cumsum_w;  // [N] sequential fp64 cumsum (NULL for unweighted)
+    int ff2_cells_on;        // D == 2: 1 when the mean leaf radius (rx + ry, prescaled units) is at most FF2_CELLS_MAX_R
+    const float* ff2c;       // D == 2 only: [ntiles][4][FF2_CELL] far-field records of a tile's four 32-point cells
     const float* mom;        // D == 1 only: [ntiles][12] far-field record of a tile: lo, hi, centre, radius, B0..B5, 0, 0
     const int* cs_index;     // [cs_buckets + 1] cs_index[b] = searchsorted(cumsum_w, b / cs_buckets * cumsum_w[N-1]): brackets the draw's search
     int cs_buckets;
@@ -145,6 +150,7 @@ struct ScoreJob {
     int cull;                // 1: skip tiles whose box proves every term flushes to zero
     const int* perm;         // visit order -> row of the query table (Morton order), or NULL
     unsigned long long* stats;   // 4 diagnostic counters, or NULL (production: nothing is counted)
+    int ff2_cells;           // D == 2 cell records: -1 per the fitted KDE, 0 / 1 forced off / on (skb_set_option("ff2_cells"))
     signed char cols[SKB_MAXD];
 };
 
@@ -239,7 +245,7 @@ cudaError_t launch_draw(const KdeDev* kde, int D, long long M, const double* u, 
                         int rcol, double rmin, double rmax, int max_attempts,
                         long long* out_idx, double* out_x, long long ld_out, double* out_z,
                         unsigned char* out_flag, unsigned long long* n_flagged, cudaStream_t st);
-cudaError_t launch_moments2(float* tiles, const float* boxes, int ntiles, cudaStream_t st);
+cudaError_t launch_moments2(float* tiles, const float* boxes, int ntiles, float* cells, KdeDev* kde_dev, cudaStream_t st);
 cudaError_t launch_moments(const float* tiles, const float* boxes, int ntiles, float* mom, cudaStream_t st);
 cudaError_t launch_cs_index(const double* cumsum, long long N, int* index, int buckets, cudaStream_t st);
 cudaError_t launch_compact(const unsigned char* flags, long long M, const void* rows, int elem_bytes,

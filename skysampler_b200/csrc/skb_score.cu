@@ -167,6 +167,59 @@ __device__ __forceinline__ double pq_fold_row(float* __restrict__ part, int row)
     return __dadd_rn(__dadd_rn(s0, s1), __dadd_rn(s2, s3));
 }
 
+// One 2-D far-field record (skb_internal.h FF2_*: centre x, y, half widths rx, ry, then B_ij, i + j <= FF2_P, row i =
+// B_i0 .. B_i,P-i) against the thread's Q queries: val = 2^(m - |s|^2) * sum B_ij sx^i sy^j, ok = the remainder bound holds
+// (2 ln2 (|sx| rx + |sy| ry) <= 1.7).  An empty record (rx < 0) is the exact value 0.  With Q == 2 both queries ride in
+// one packed fp32x2 Horner chain, the coefficient being the broadcast operand.
+template <int Q>
+__device__ __forceinline__ void ff2_eval(const float* __restrict__ rec, const float (&q2)[Q][2], const float (&nm2)[Q],
+                                         float (&val)[Q], bool (&ok)[Q])
+{
+    const float4 cr = *reinterpret_cast<const float4*>(rec);
+    const float* __restrict__ B = rec + 4;
+    float sx[Q], sy[Q], p[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) { sx[q] = q2[q][0] - cr.x; sy[q] = q2[q][1] - cr.y; p[q] = 0.f; }
+    if constexpr (Q == 2) {
+        const u64 sx2 = pk(sx[0], sx[1]), sy2 = pk(sy[0], sy[1]);
+        u64 p2 = pk(0.f, 0.f);
+#pragma unroll
+        for (int i = FF2_P; i >= 0; i--) {
+            const int n = FF2_P + 1 - i;
+            const int off = i * (FF2_P + 1) - (i * (i - 1)) / 2;
+            u64 in2 = pk(B[off + n - 1], B[off + n - 1]);
+#pragma unroll
+            for (int j = n - 2; j >= 0; j--) in2 = fma2(in2, sy2, pk(B[off + j], B[off + j]));
+            p2 = fma2(p2, sx2, in2);
+        }
+        upk(p2, p[0], p[1]);
+    } else {
+#pragma unroll
+        for (int i = FF2_P; i >= 0; i--) {
+            const int n = FF2_P + 1 - i;
+            const int off = i * (FF2_P + 1) - (i * (i - 1)) / 2;
+            float in[Q];
+#pragma unroll
+            for (int q = 0; q < Q; q++) in[q] = B[off + n - 1];
+#pragma unroll
+            for (int j = n - 2; j >= 0; j--) {
+                const float b = B[off + j];
+#pragma unroll
+                for (int q = 0; q < Q; q++) in[q] = fmaf(in[q], sy[q], b);
+            }
+#pragma unroll
+            for (int q = 0; q < Q; q++) p[q] = fmaf(p[q], sx[q], in[q]);
+        }
+    }
+    const bool empty = cr.z < 0.f;
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        const float v = ex2_neg(fmaf(sy[q], sy[q], fmaf(sx[q], sx[q], nm2[q]))) * p[q];
+        val[q] = empty ? 0.f : v;
+        ok[q] = empty || (fabsf(sx[q]) * cr.z + fabsf(sy[q]) * cr.w <= FF2_SR_MAX);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // The score kernel.  grid = (query blocks, jobs, training splits), block = NT threads.
 // ---------------------------------------------------------------------------------------------
@@ -191,7 +244,11 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
     float* stages = reinterpret_cast<float*>(smem_raw);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NSTAGE * STAGE_BYTES);
     uint64_t* empty_bar = full_bar + NSTAGE;
-    unsigned* need_bits = reinterpret_cast<unsigned*>(empty_bar + NSTAGE);   // one bit per tile: some warp needs it
+    // D == 2 (culled instantiation): staging buffer for the four cell records of a tile, between the barriers and the bitmap
+    constexpr size_t CELL_BYTES = (D == 2 && Q == queries_per_thread(2)) ? (size_t)4 * FF2_CELL * sizeof(float) : 0;
+    static_assert((2 * NSTAGE * sizeof(uint64_t)) % 16 == 0 || CELL_BYTES == 0, "cell buffer alignment");
+    float* cellbuf = reinterpret_cast<float*>(empty_bar + NSTAGE);
+    unsigned* need_bits = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(empty_bar + NSTAGE) + CELL_BYTES);   // one bit per tile: some warp needs it
     __shared__ int s_last[QB / FB];
 
     const int tid = threadIdx.x;
@@ -233,6 +290,9 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
     float bmin[Q];          // running estimate of the smallest weighted exponent seen (absolute)
     const float ref_bias = kde->ref_bias;
     home_reference<D, Q>(kde, ntiles, q2, bmin, mref, nm2);
+    // D == 2: second-level (cell) far-field records on?  A property of the fitted KDE (its leaves must be narrow enough for
+    // the cells to serve what the tile record cannot), or forced either way for A/B runs
+    const bool use_cells = (D == 2) && kde->ff2c != nullptr && (job.ff2_cells < 0 ? kde->ff2_cells_on != 0 : job.ff2_cells != 0);
 
     // ---- which tiles does this CTA need at all?  A tile that every warp can already cull with its initial
     // references is never requested from L2 (references only move down, so this is conservative).  Two
@@ -326,7 +386,8 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
     }
 
     for (int it = 0;; it++) {
-        if (next_tile(cw, cbits) < 0) break;
+        const int trel = next_tile(cw, cbits);           // tile index within this split
+        if (trel < 0) break;
         n_visited++;
         const int s = it % NSTAGE;
         const uint32_t ph = (it / NSTAGE) & 1;
@@ -391,52 +452,63 @@ skb_score_kernel(const __grid_constant__ ScoreLaunch L)
         for (int q = 0; q < Q; q++) { ffq[q] = false; ffv[q] = 0.f; }
         if constexpr (D == 2 && Q == queries_per_thread(2)) {
             if (job.cull) {
-                const float* hdr = tile + (D + 1) * TN;
-                const float4 cr = *reinterpret_cast<const float4*>(hdr + FF2_OFF);     // cx, cy, rx, ry (rx < 0: no record)
-                const float* B = hdr + FF2_OFF + 4;
-                float sx[Q], sy[Q], p[Q];
-#pragma unroll
-                for (int q = 0; q < Q; q++) { sx[q] = q2[q][0] - cr.x; sy[q] = q2[q][1] - cr.y; p[q] = 0.f; }
-                if constexpr (Q == 2) {
-                    // the thread's two queries ride in one packed fp32x2 Horner chain (the coefficient is the broadcast operand)
-                    const u64 sx2 = pk(sx[0], sx[1]), sy2 = pk(sy[0], sy[1]);
-                    u64 p2 = pk(0.f, 0.f);
-#pragma unroll
-                    for (int i = FF2_P; i >= 0; i--) {
-                        const int n = FF2_P + 1 - i;                                  // row i holds B_i0 .. B_i,n-1
-                        const int off = i * (FF2_P + 1) - (i * (i - 1)) / 2;
-                        u64 in2 = pk(B[off + n - 1], B[off + n - 1]);
-#pragma unroll
-                        for (int j = n - 2; j >= 0; j--) in2 = fma2(in2, sy2, pk(B[off + j], B[off + j]));
-                        p2 = fma2(p2, sx2, in2);
-                    }
-                    upk(p2, p[0], p[1]);
-                } else {
-#pragma unroll
-                    for (int i = FF2_P; i >= 0; i--) {
-                        const int n = FF2_P + 1 - i;
-                        const int off = i * (FF2_P + 1) - (i * (i - 1)) / 2;
-                        float in[Q];
-#pragma unroll
-                        for (int q = 0; q < Q; q++) in[q] = B[off + n - 1];
-#pragma unroll
-                        for (int j = n - 2; j >= 0; j--) {
-                            const float b = B[off + j];
-#pragma unroll
-                            for (int q = 0; q < Q; q++) in[q] = fmaf(in[q], sy[q], b);
-                        }
-#pragma unroll
-                        for (int q = 0; q < Q; q++) p[q] = fmaf(p[q], sx[q], in[q]);
-                    }
-                }
+                float tv[Q];
+                bool tok[Q];
+                ff2_eval<Q>(tile + (D + 1) * TN + FF2_OFF, q2, nm2, tv, tok);
                 bool all = true;
 #pragma unroll
                 for (int q = 0; q < Q; q++) {
-                    const float v = ex2_neg(fmaf(sy[q], sy[q], fmaf(sx[q], sx[q], nm2[q]))) * p[q];
-                    const bool crit = (fabsf(sx[q]) * cr.z + fabsf(sy[q]) * cr.w <= FF2_SR_MAX) && (cr.z >= 0.f);
-                    ffq[q] = own_cull[q] || (crit && (v < OVERFLOW_LIMIT));
-                    ffv[q] = own_cull[q] ? 0.f : v;
+                    ffq[q] = own_cull[q] || (tok[q] && (tv[q] < OVERFLOW_LIMIT));
+                    ffv[q] = own_cull[q] ? 0.f : tv[q];
                     all &= ffq[q];
+                }
+                // second level: the tile's four 32-point cells (median splits of the leaf, skb_fit.cu) carry records of their
+                // own with half the radius; a query the tile record cannot serve is served when ALL FOUR cell records can
+                bool try_cells = false;
+                if (!__all_sync(0xffffffffu, all) && use_cells) {
+                    // the cell records are fetched when some query still unserved passes all four of its remainder bounds (a
+                    // query's own path never depends on its companions: it is served by the cells iff ITS bounds hold)
+                    const float4* __restrict__ hdrs = reinterpret_cast<const float4*>(kde->ff2c + (size_t)(t0 + trel) * (4 * FF2_CELL));
+                    bool pre[Q];
+#pragma unroll
+                    for (int q = 0; q < Q; q++) pre[q] = !ffq[q];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const float4 cr = __ldg(hdrs + c * (FF2_CELL / 4));
+#pragma unroll
+                        for (int q = 0; q < Q; q++)
+                            pre[q] &= (cr.z < 0.f) || (fabsf(q2[q][0] - cr.x) * cr.z + fabsf(q2[q][1] - cr.y) * cr.w <= FF2_SR_MAX);
+                    }
+                    bool want = false;
+#pragma unroll
+                    for (int q = 0; q < Q; q++) want |= pre[q];
+                    try_cells = __any_sync(0xffffffffu, want);
+                }
+                if (try_cells) {
+                    const float4* __restrict__ src = reinterpret_cast<const float4*>(kde->ff2c + (size_t)(t0 + trel) * (4 * FF2_CELL));
+                    float4* dst = reinterpret_cast<float4*>(cellbuf);
+#pragma unroll
+                    for (int i = 0; i < 4 * FF2_CELL / 4 / 32; i++) dst[lane + 32 * i] = __ldg(src + lane + 32 * i);
+                    __syncwarp();
+                    float cv[Q];
+                    bool cok[Q];
+#pragma unroll
+                    for (int q = 0; q < Q; q++) { cv[q] = 0.f; cok[q] = true; }
+#pragma unroll 1
+                    for (int c = 0; c < 4; c++) {
+                        float v[Q];
+                        bool ok[Q];
+                        ff2_eval<Q>(cellbuf + c * FF2_CELL, q2, nm2, v, ok);
+#pragma unroll
+                        for (int q = 0; q < Q; q++) { cv[q] += v[q]; cok[q] = cok[q] && ok[q]; }
+                    }
+                    __syncwarp();
+                    all = true;
+#pragma unroll
+                    for (int q = 0; q < Q; q++) {
+                        if (!ffq[q] && cok[q] && (cv[q] < OVERFLOW_LIMIT)) { ffq[q] = true; ffv[q] = cv[q]; }
+                        all &= ffq[q];
+                    }
                 }
                 if (__all_sync(0xffffffffu, all)) {
 #pragma unroll
@@ -956,7 +1028,7 @@ static cudaError_t launch_score_dq(const ScoreLaunch& L, int njobs, long long ma
     } else {
         constexpr int NSTAGE = nstage(D);
         const size_t smem = (size_t)NSTAGE * stage_floats(D) * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t) +
-                            (((size_t)max_ntiles + 31) / 32) * 4 + 16;
+                            (((size_t)max_ntiles + 31) / 32) * 4 + 16 + (D == 2 ? (size_t)4 * FF2_CELL * 4 : 0);
         cudaError_t e = cudaFuncSetAttribute(skb_score_kernel<D, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         skb_score_kernel<D, Q><<<grid, NT, smem, st>>>(L);

@@ -1,2 +1,3 @@
-python -m pytest tests/test_gpu_large.py -m gpu -x -q -k "d2 or splits" 2>&1 | tail -3
-python tools/perf_scan.py 2 1000000 2>&1 | grep -v Warn
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python tools/perf_scan.py 1,2,3,4 1000000 2>&1 | grep -v Warn
+python tools/perf_scan.py 1,2,3,4 100000 2>&1 | grep -v Warn
