@@ -66,6 +66,9 @@ namespace skb {
 #ifndef SKB_PQ_MINB
 #define SKB_PQ_MINB 22        // launch bound (CTAs per SM) of the PQ kernel for D <= 8 (96 registers)
 #endif
+#ifndef SKB_PQ_COOP_SCAN
+#define SKB_PQ_COOP_SCAN 0     // 1: the home tiles are scanned by the whole warp, one query at a time
+#endif
 #ifndef SKB_PQ_MINB_TOP
 #define SKB_PQ_MINB_TOP 16    // D > 12 (128 registers)
 #endif
@@ -650,7 +653,44 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
     mref[0] = 0.f; S[0] = 0.0; nm2[0] = 0.f;
     const float ref_bias = kde->ref_bias;
     const float PQ_LIMIT = exp2f((float)SKB_PQ_SLACK - ref_bias);     // a lane term this large re-centres
+#if SKB_PQ_COOP_SCAN
+    // exponent reference: the home super-box by branch and bound with one query per lane; its tiles are then scanned by the
+    // WHOLE warp, one query at a time (lanes = tiles for the box tests, lanes = points for the scans: coalesced 256-byte rows
+    // instead of 32 private tile walks), nearest box first, while a tile's box can still beat the best point found.  The
+    // result is the exact minimum over the home super-box, as before.
+    {
+        int sbest[1];
+        home_superbox<D, 1>(kde, q2, sbest);
+        const bool has_w = kde->has_w != 0;
+        float mine = INFINITY;
+#pragma unroll 1
+        for (int src = 0; src < 32; src++) {
+            float zq[D];
+#pragma unroll
+            for (int k = 0; k < D; k++) zq[k] = __shfl_sync(FULL, q2[0][k], src);
+            const int si = __shfl_sync(FULL, sbest[0], src);
+            const int t = si * SG + (lane & 15);
+            const float lbt = (lane < SG && t < ntiles) ? box_lb<D>(kde->boxes + (size_t)t * 2 * D, zq) : INFINITY;
+            float best = INFINITY;
+            unsigned todo = __ballot_sync(FULL, lbt < INFINITY);
+            while (todo) {
+                float v = ((todo >> lane) & 1u) ? lbt : INFINITY;
+                int l = lane;
+                warp_argmin(v, l);
+                if (!(v < best)) break;
+                todo &= ~(1u << l);
+                best = fminf(best, coop_scan_tile<D>(kde->tiles + (size_t)(si * SG + (l & 15)) * STAGE_FLOATS, zq, has_w, lane));
+            }
+            if (lane == src) mine = best;
+        }
+        if (!(mine < 1.0e30f)) mine = ref_bias;                   // inf/NaN rows (or padding only): finite reference
+        bmin[0] = mine;
+        mref[0] = floorf(mine) - ref_bias;
+        nm2[0] = -mref[0];
+    }
+#else
     home_reference<D, Q>(kde, ntiles, q2, bmin, mref, nm2);
+#endif
 
 #pragma unroll
     for (int k = 0; k < D; k++) rows[lane * QS + k] = q2[0][k];

@@ -459,6 +459,52 @@ __device__ __forceinline__ float scan_tile_min(const float* __restrict__ tile, c
     return best;
 }
 
+// ---- warp-cooperative helpers (lanes = boxes / points) ----
+template <int D>
+__device__ __forceinline__ float box_lb(const float* __restrict__ b, const float (&zq)[D])
+{
+    float lb = 0.f;
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        const float lo = __ldg(b + k), hi = __ldg(b + D + k);
+        const float gap = fmaxf(fmaxf(lo - zq[k], zq[k] - hi), 0.f);      // empty boxes are (inf, -inf): gap = inf
+        lb = fmaf(gap, gap, lb);
+    }
+    return lb;
+}
+
+// min over a tile of the weighted exponent |c dz|^2 - log2 w, lanes = points (warp cooperative, warp-uniform result)
+template <int D>
+__device__ __forceinline__ float coop_scan_tile(const float* __restrict__ tile, const float (&zq)[D], bool has_w, int lane)
+{
+    constexpr int TN = tile_points(D);
+    float b = INFINITY;
+#pragma unroll
+    for (int p = lane; p < TN; p += 32) {
+        float a = has_w ? fminf(-__log2f(__ldg(tile + D * TN + p)), LW_CAP) : 0.f;
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            const float d = zq[k] - __ldg(tile + k * TN + p);
+            a = fmaf(d, d, a);
+        }
+        b = fminf(b, a);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b = fminf(b, __shfl_xor_sync(0xffffffffu, b, o));
+    return b;
+}
+
+// (value, index) argmin over the warp; ties keep the smaller index; result is warp uniform
+__device__ __forceinline__ void warp_argmin(float& v, int& i)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+}
+
 // Reference exponents, per query and independent of split / batch / GPU:
 //  (1) nearest super-box (SG consecutive kd leaves) by box distance, then the nearest tile box inside
 //      it: the query's "home" tile;
@@ -466,20 +512,15 @@ __device__ __forceinline__ float scan_tile_min(const float* __restrict__ tile, c
 //      upper bound of the true minimum, and the true nearest neighbour usually lives in the home tile,
 //      so the reference is tight from the first tile on — tight references are what lets the box test
 //      cull.  (If a closer point turns up later the reference is tightened / recentred on the fly.)
+// (1) of the reference search: the super-box nearest to each of the thread's queries, exact branch and bound over the chunk
+// boxes (ties keep the first)
 template <int D, int Q>
-__device__ __forceinline__ void home_reference(const KdeDev* __restrict__ kde, int ntiles, const float (&q2)[Q][D],
-                                               float (&bmin)[Q], float (&mref)[Q], float (&nm2)[Q], bool alive = true)
+__device__ __forceinline__ void home_superbox(const KdeDev* __restrict__ kde, const float (&q2)[Q][D], int (&sbest)[Q], bool alive = true)
 {
-    constexpr int TN = tile_points(D);
-    constexpr int STAGE_FLOATS = stage_floats(D);
+    const float* __restrict__ sbx = kde->sboxes;
+    const int nsuper = kde->nsuper;
     {
-        const float* __restrict__ sbx = kde->sboxes;
-        const float* __restrict__ bx = kde->boxes;
-        const int nsuper = kde->nsuper;
-        const bool has_w = kde->has_w != 0;
-        const float ref_bias = kde->ref_bias;
         float lbbest[Q];
-        int sbest[Q];
 #pragma unroll
         for (int q = 0; q < Q; q++) { lbbest[q] = INFINITY; sbest[q] = 0; }
         // branch and bound over the chunk boxes: a chunk whose box is no closer than the best super-box so
@@ -527,6 +568,23 @@ __device__ __forceinline__ void home_reference(const KdeDev* __restrict__ kde, i
                 }
             }
         }
+    }
+}
+
+template <int D, int Q>
+__device__ __forceinline__ void home_reference(const KdeDev* __restrict__ kde, int ntiles, const float (&q2)[Q][D],
+                                               float (&bmin)[Q], float (&mref)[Q], float (&nm2)[Q], bool alive = true)
+{
+    constexpr int TN = tile_points(D);
+    constexpr int STAGE_FLOATS = stage_floats(D);
+    {
+        const float* __restrict__ sbx = kde->sboxes;
+        const float* __restrict__ bx = kde->boxes;
+        const int nsuper = kde->nsuper;
+        const bool has_w = kde->has_w != 0;
+        const float ref_bias = kde->ref_bias;
+        int sbest[Q];
+        home_superbox<D, Q>(kde, q2, sbest, alive);
 #pragma unroll
         for (int q = 0; q < Q; q++) {
             if (!alive) { bmin[q] = ref_bias; mref[q] = 0.f; nm2[q] = 0.f; continue; }

@@ -107,51 +107,6 @@ __device__ __forceinline__ int nth_set_bit(unsigned w, unsigned n)
     return pos;
 }
 
-template <int D>
-__device__ __forceinline__ float box_lb(const float* __restrict__ b, const float (&zq)[D])
-{
-    float lb = 0.f;
-#pragma unroll
-    for (int k = 0; k < D; k++) {
-        const float lo = __ldg(b + k), hi = __ldg(b + D + k);
-        const float gap = fmaxf(fmaxf(lo - zq[k], zq[k] - hi), 0.f);      // empty boxes are (inf, -inf): gap = inf
-        lb = fmaf(gap, gap, lb);
-    }
-    return lb;
-}
-
-// min over a tile of the weighted exponent |c dz|^2 - log2 w, lanes = points (warp cooperative, warp-uniform result)
-template <int D>
-__device__ __forceinline__ float coop_scan_tile(const float* __restrict__ tile, const float (&zq)[D], bool has_w, int lane)
-{
-    constexpr int TN = tile_points(D);
-    float b = INFINITY;
-#pragma unroll
-    for (int p = lane; p < TN; p += 32) {
-        float a = has_w ? fminf(-__log2f(__ldg(tile + D * TN + p)), LW_CAP) : 0.f;
-#pragma unroll
-        for (int k = 0; k < D; k++) {
-            const float d = zq[k] - __ldg(tile + k * TN + p);
-            a = fmaf(d, d, a);
-        }
-        b = fminf(b, a);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) b = fminf(b, __shfl_xor_sync(0xffffffffu, b, o));
-    return b;
-}
-
-// (value, index) argmin over the warp; ties keep the smaller index; result is warp uniform
-__device__ __forceinline__ void warp_argmin(float& v, int& i)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, i, o);
-        if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
-    }
-}
-
 // Exponent reference of ONE query (coordinates broadcast to the warp), warp cooperative with lanes = boxes / points:
 //   (1) the super-box nearest to the query by box distance (exact branch and bound over chunk boxes -> super-boxes): "home";
 //   (2) its tiles are scanned in order of box distance for the smallest weighted exponent |c dz|^2 - log2 w, as long as a
