@@ -722,12 +722,12 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
 #pragma unroll
             for (int k = 0; k < D; k++) zq[k] = q2[0][k];
             if (cull) {
-                const float* b = cbx + (size_t)(s_base / PQ_CH) * 2 * D;
+                float lo[D], hi[D];
+                load_box<D>(cbx + (size_t)(s_base / PQ_CH) * 2 * D, lo, hi);
                 float lb = 0.f;
 #pragma unroll
                 for (int k = 0; k < D; k++) {
-                    const float lo = __ldg(b + k), hi = __ldg(b + D + k);
-                    const float gap = fmaxf(fmaxf(lo - zq[k], zq[k] - hi), 0.f);
+                    const float gap = fmaxf(fmaxf(lo[k] - zq[k], zq[k] - hi[k]), 0.f);
                     lb = fmaf(gap, gap, lb);
                 }
                 if (!__any_sync(FULL, !(lb - mref[0] > CULL_MARGIN))) continue;
@@ -735,14 +735,13 @@ skb_score_pq_kernel(const __grid_constant__ ScoreLaunch L)
             const int nsb = s_end - s_base < PQ_CH ? s_end - s_base : PQ_CH;
 #pragma unroll 2
             for (int j = 0; j < nsb; j++) {
-                const float* b = sbx + (size_t)(s_base + j) * 2 * D;
+                float lo[D], hi[D];
+                load_box<D>(sbx + (size_t)(s_base + j) * 2 * D, lo, hi);
                 float lb = 0.f;
-                bool valid = true;
+                const bool valid = (lo[0] <= hi[0]);
 #pragma unroll
                 for (int k = 0; k < D; k++) {
-                    const float lo = __ldg(b + k), hi = __ldg(b + D + k);
-                    if (k == 0) valid = (lo <= hi);
-                    const float gap = fmaxf(fmaxf(lo - zq[k], zq[k] - hi), 0.f);
+                    const float gap = fmaxf(fmaxf(lo[k] - zq[k], zq[k] - hi[k]), 0.f);
                     lb = fmaf(gap, gap, lb);
                 }
                 const bool need = valid && (!cull || !(lb - mref[0] > CULL_MARGIN));

@@ -459,6 +459,31 @@ __device__ __forceinline__ float scan_tile_min(const float* __restrict__ tile, c
     return best;
 }
 
+// one bounding box (lo[D], hi[D], 2 D consecutive floats; box tables are 16-byte aligned when D is even) with vector loads
+template <int D>
+__device__ __forceinline__ void load_box(const float* __restrict__ b, float (&lo)[D], float (&hi)[D])
+{
+    if constexpr (D % 4 == 0) {
+#pragma unroll
+        for (int k = 0; k < D; k += 4) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(b + k));
+            const float4 c = __ldg(reinterpret_cast<const float4*>(b + D + k));
+            lo[k] = a.x; lo[k + 1] = a.y; lo[k + 2] = a.z; lo[k + 3] = a.w;
+            hi[k] = c.x; hi[k + 1] = c.y; hi[k + 2] = c.z; hi[k + 3] = c.w;
+        }
+    } else if constexpr (D % 2 == 0) {
+#pragma unroll
+        for (int k = 0; k < D; k += 2) {
+            const float2 a = __ldg(reinterpret_cast<const float2*>(b + k));
+            const float2 c = __ldg(reinterpret_cast<const float2*>(b + D + k));
+            lo[k] = a.x; lo[k + 1] = a.y; hi[k] = c.x; hi[k + 1] = c.y;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < D; k++) { lo[k] = __ldg(b + k); hi[k] = __ldg(b + D + k); }
+    }
+}
+
 // ---- warp-cooperative helpers (lanes = boxes / points) ----
 template <int D>
 __device__ __forceinline__ float box_lb(const float* __restrict__ b, const float (&zq)[D])
@@ -533,7 +558,7 @@ __device__ __forceinline__ void home_superbox(const KdeDev* __restrict__ kde, co
             {
                 float lo[D], hi[D];
 #pragma unroll
-                for (int k = 0; k < D; k++) { lo[k] = __ldg(cbx + (size_t)cidx * 2 * D + k); hi[k] = __ldg(cbx + (size_t)cidx * 2 * D + D + k); }
+                for (int k = 0; k < 1; k++) load_box<D>(cbx + (size_t)cidx * 2 * D, lo, hi);
 #pragma unroll
                 for (int q = 0; q < Q; q++) {
                     float lb = 0.f;
@@ -553,7 +578,7 @@ __device__ __forceinline__ void home_superbox(const KdeDev* __restrict__ kde, co
             for (int sidx = cidx * CG; sidx < send; sidx++) {
                 float lo[D], hi[D];
 #pragma unroll
-                for (int k = 0; k < D; k++) { lo[k] = __ldg(sbx + (size_t)sidx * 2 * D + k); hi[k] = __ldg(sbx + (size_t)sidx * 2 * D + D + k); }
+                for (int k = 0; k < 1; k++) load_box<D>(sbx + (size_t)sidx * 2 * D, lo, hi);
                 if (!(lo[0] <= hi[0])) continue;
 #pragma unroll
                 for (int q = 0; q < Q; q++) {
