@@ -14,7 +14,7 @@ typedef unsigned long long u64;
 //   row whose first 2D words are the tile's bounding box (lo[D], hi[D]),
 // so that ONE 1-D TMA bulk copy (cp.async.bulk, SASS UBLKCP) moves a whole tile into shared memory
 // and an LDS.128 of row k yields two packed {x_j, x_j+1} operands for FADD2/FFMA2.
-// Tiles are the leaves of a kd-tree over the training points (built on the host at fit time), so a
+// Tiles are the leaves of a kd-tree over the training points (built on the device at fit time), so a
 // tile is spatially compact and its box test can prove that every pair term flushes to zero.
 #ifndef SKB_TN_LO
 #define SKB_TN_LO 128
@@ -37,13 +37,7 @@ __host__ __device__ constexpr int tile_points(int D) { return D <= 2 ? SKB_TN_LO
 #ifndef SKB_NSTAGE_HI
 #define SKB_NSTAGE_HI 2
 #endif
-#ifndef SKB_NSTAGE_PQ
-#define SKB_NSTAGE_PQ 1
-#endif
-// TMA ring depth (shared memory per CTA = depth x tile bytes) of the lanes = queries kernel.  The per-query
-// kernel (D >= 5, culling on) copies a tile into registers on arrival and hands its stage back at once, so
-// ONE stage (SKB_NSTAGE_PQ) already overlaps the next copy with the whole pair loop — and that kernel's speed
-// follows the number of resident warps (one stage: 22 one-warp CTAs per SM at d = 8).
+// TMA ring depth (shared memory per CTA = depth x tile bytes) of the lanes = queries kernel.
 __host__ __device__ constexpr int nstage(int D) { return D <= 4 ? SKB_NSTAGE : SKB_NSTAGE_HI; }
 #ifndef SKB_NT
 #define SKB_NT 32

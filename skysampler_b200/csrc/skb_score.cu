@@ -4,14 +4,15 @@
 //
 // Every (query, training point) pair is accounted for — no tolerance:
 //     log p(z) = log_norm + log sum_j w_j exp(-|z - z_j|^2 / 2h^2)
-// with fp32 pair terms and an fp64 log-sum-exp state per query.
+// with fp32 pair terms and an fp64 log-sum-exp state per query (d <= 2: a tile's terms may be summed through its
+// far-field record where a rigorous remainder bound keeps that as exact as the fp32 pair loop, see below).
 //
 // Arithmetic.  Per evaluated pair the FMA pipe sees exactly 2D+1 lane operations (D subtractions, D fused
 // squares, one weighted accumulate) and the SFU one EX2:
 //   * coordinates are prescaled by c = sqrt(log2(e)/2)/h so that exp(-d^2/2h^2) = exp2(-|c dz|^2);
 //   * the per-query reference exponent m is folded into the accumulator seed (acc starts at -m), so no
 //     per-pair shift is needed; m only has to lie in a ~216-binade window around the true minimum
-//     distance.  It comes from an exact evaluation of the query's home tile and is tightened from the
+//     distance.  It comes from an exact evaluation of the query's home tiles and is tightened from the
 //     exponents of the block sums; a 64-point block whose fp32 partial sum overflows is re-run after a
 //     min-only pass over that block (rare);
 //   * the weight is applied as sum = fma(w_j, e, sum) — same cost as an add;
@@ -21,21 +22,22 @@
 // Culling.  Training tiles are kd-tree leaves with bounding boxes (three levels: tile, super-box of 16 tiles,
 // chunk of 16 super-boxes) and a warp's queries are Morton neighbours: a tile whose box is > 128 binades
 // beyond a query's reference has only terms that flush to zero in the arithmetic above and is skipped.
-// Two kernels:
+// Kernels of this file (the sorted-incidence pipeline for d = 3..5 lives in skb_sparse.cu):
+//   skb_score_d1_kernel     d = 1: sorted intervals, one far-field record per tile (comment above the kernel).
 //   skb_score_kernel<D,Q>   lanes = queries (Q whole queries per thread, tile words broadcast by LDS.128, no
-//                           cross-lane reduction); a tile is evaluated when ANY query of the warp needs it.
-//                           Used for D <= 4 and, with larger Q, whenever culling is off.
-//   skb_score_pq_kernel<D>  D >= 5: lanes = two training points each; box tests one tile per lane; only the
-//                           queries that need a tile are evaluated (see the comment above the kernel).
-// Data movement.  One warp per CTA; its needed tiles arrive in shared memory through a private ring of
-// 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx).
+//                           cross-lane reduction); a tile is evaluated when ANY query of the warp needs it; tiles
+//                           arrive in shared memory through a private ring of 1-D TMA bulk copies (cp.async.bulk +
+//                           mbarrier complete_tx).  d = 2 (with two levels of far-field records), KDEs of <= 512 tiles,
+//                           and, with larger Q, every dimension when culling is off.
+//   skb_score_pq_kernel<D>  d >= 6: lanes = two training points each, read straight from L2; box tests one tile per
+//                           lane; only the queries that need a tile are evaluated (comment above the kernel).
 
 #include "skb_score_common.cuh"
 
 namespace skb {
 
 // ---------------------------------------------------------------------------------------------
-// Per-query culling ("PQ") kernel for D >= SKB_PQ_MIN_D.  With lanes = queries a tile is evaluated for all 32
+// Per-query culling ("PQ") kernel, instantiated for D >= SKB_PQ_MIN_D and routed for D >= 6 (skb_api.cu).  With lanes = queries a tile is evaluated for all 32
 // queries of the warp as soon as ONE of them needs it; in 8-D a query needs ~1.2 % of the kd leaves but the
 // union over a warp's 32 Morton neighbours is ~5 %, so 3/4 of the pairs evaluated that way are terms that
 // flush to zero.  This kernel turns the warp around:
@@ -43,8 +45,8 @@ namespace skb {
 //     per lane tests the super-boxes (ballot = which queries need it); then one TILE per lane tests its box
 //     against exactly those queries (coordinates broadcast from shared memory) and the non-empty
 //     (tile, query mask) pairs are compacted into a work list in shared memory;
-//   * the work list is streamed through the TMA ring.  Every lane keeps TWO training points of the 64-point
-//     tile in registers (one packed fp32x2 operand per dimension) and the tile's query mask is walked bit by
+//   * the work list is streamed: every lane reads TWO training points of the 64-point tile straight from L2
+//     (coalesced LDG.64 rows; no shared-memory staging) and keeps them in registers (one packed fp32x2 operand per dimension) and the tile's query mask is walked bit by
 //     bit: only the queries that need the tile are evaluated.  Lane l adds its two terms to part[query][l]
 //     (fp32, shared memory); rows are folded into the owner lane's fp64 (m, S) state at fixed tile-index
 //     boundaries (every 2^PQ_EPOCH_SHIFT tiles) in a fixed order.
