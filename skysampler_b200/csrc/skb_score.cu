@@ -66,7 +66,7 @@ namespace skb {
 #define SKB_PQ_MIN_D 5
 #endif
 #ifndef SKB_PQ_MINB
-#define SKB_PQ_MINB 22        // launch bound (CTAs per SM) of the PQ kernel for D <= 8 (96 registers)
+#define SKB_PQ_MINB 24        // launch bound (CTAs per SM) of the PQ kernel for D <= 8 (80 registers; 22.6 vs 23.2 ms at 22, 23.2 at 26: spills)
 #endif
 #ifndef SKB_PQ_COOP_SCAN
 #define SKB_PQ_COOP_SCAN 1     // 1: the home tiles are scanned by the whole warp, one query at a time (d=8 24.4 -> 23.4 ms); 0: one private walk per lane
