@@ -128,10 +128,10 @@ class GaussianKDE(object):
         return self._h
 
     # -- scoring ----------------------------------------------------------------------------------
-    def score_samples(self, X, cols=None, is_whitened=True, out=None, stream=None, _validated=False):
+    def score_samples(self, X, cols=None, is_whitened=True, out=None, stream=None):
         """log p(X): float64 ndarray for host input, torch CUDA tensor for CUDA input (zero copy)."""
         h = self._handle()
-        X = _as_matrix(X, check_finite=not _validated)
+        X = _as_matrix(X)
         m, ld = X.shape
         if cols is None and ld != self.ndim_:
             raise ValueError("X has %d features, but GaussianKDE is expecting %d features as input." % (ld, self.ndim_))
@@ -430,14 +430,15 @@ class KDEContainer(object):
 
     def score_samples(self, arr):
         """Assuming that arr is in the data format (emulator.py:380-385): columns are positional."""
+        # (the finiteness check runs once, inside the KDE's own score_samples)
         if isinstance(arr, (pd.DataFrame, pd.Series)) or isinstance(arr, np.ndarray) or _cabi._is_torch(arr):
-            X = _as_matrix(arr)
+            X = _as_matrix(arr, check_finite=False)
         else:
-            X = _as_matrix(np.asarray(arr))
+            X = _as_matrix(np.asarray(arr), check_finite=False)
         if X.shape[1] != self.ndim:
             raise ValueError("X has %d features, but KDEContainer is expecting %d features as input."
                              % (X.shape[1], self.ndim))
-        res = self.kde.score_samples(X, is_whitened=False, _validated=True)      # X went through _as_matrix above
+        res = self.kde.score_samples(X, is_whitened=False)
         return res, self._jacobian_det
 
     def drop_kde(self):
