@@ -75,3 +75,24 @@ def test_product_code_never_imports_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert not re.search(r"^\s*(from|import)\s+sklearn\.neighbors", src, flags=re.M), f
                 assert "KernelDensity(" not in src.replace("KernelDensity(...)", ""), f
+
+
+def test_diagnostic_options_round_trip_without_a_gpu():
+    """skb_set_option / skb_get_option are host-side switches (include/skb.h): every documented name is known, values
+    are normalised, unknown names fail with SKB_EINVAL and -1."""
+    lib = _cabi.lib()
+    header = open(os.path.join(ROOT, "include", "skb.h")).read()
+    for name, probe, back in (("cull", 0, 0), ("cull", 7, 1), ("force_nsplit", 5, 5), ("force_nsplit", -3, 0),
+                              ("stats", 1, 1), ("stats", 0, 0), ("kernel", 2, 2), ("kernel", 0, 0),
+                              ("ff2_cells", 0, 0), ("ff2_cells", 9, 1), ("ff2_cells", -1, -1),
+                              ("host_stage_rows", 4096, 4096), ("host_stage_rows", 0, 0)):
+        assert '"%s"' % name in header, name
+        old = lib.skb_get_option(name.encode())
+        assert lib.skb_set_option(name.encode(), probe) == 0
+        assert lib.skb_get_option(name.encode()) == back, (name, probe)
+        assert lib.skb_set_option(name.encode(), old) == 0
+    assert lib.skb_set_option(b"no_such_switch", 1) == _cabi.SKB_EINVAL and b"unknown option" in lib.skb_last_error()
+    assert lib.skb_get_option(b"no_such_switch") == -1
+    with _cabi.option("cull", 0):
+        assert lib.skb_get_option(b"cull") == 0
+    assert lib.skb_get_option(b"cull") == 1
