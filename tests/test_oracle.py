@@ -173,3 +173,45 @@ def test_c_brute_force_twin_matches_the_numpy_oracle():
         ma, sa = brute64.partial_lse(z, w, h, q)
         mb, sb = cbrute.partial_lse(z, w, h, q)
         assert np.array_equal(ma, mb) and np.allclose(sa, sb, rtol=1e-12, atol=0)
+
+
+def test_far_field_record_remainder_bound_and_fp32_evaluation():
+    """The admission rules of the d <= 2 far-field paths (1-D: P = 5, z <= 1/4; 2-D: P = 12, z <= 1.7) rest on the bound
+    z^(P+1)/(P+1)! e^(2z) for the record's relative error.  Checked here in fp64 on random tiles (it must hold for EVERY
+    point layout), together with the fp32 Horner evaluation the kernels run (error << the 1e-4 contract)."""
+    from oracle import farfield_model as ff
+    rs = np.random.RandomState(12)
+    assert ff.remainder_bound(0.25, 5) < 6e-7 and ff.remainder_bound(1.7, 12) < 5e-6
+    worst = {1: 0.0, 2: 0.0}
+    worst32 = {1: 0.0, 2: 0.0}
+    for d, P, zmax in ((1, 5, 0.25), (2, 12, 1.7)):
+        for trial in range(300):
+            n = int(rs.randint(1, 129))
+            r = 10.0 ** rs.uniform(-3, 0.3, size=d)                       # half widths of the tile
+            layout = trial % 3
+            if layout == 0:
+                t = rs.uniform(-1, 1, size=(n, d)) * r
+            elif layout == 1:                                             # everything in the corners: the bound's worst case
+                t = rs.choice([-1.0, 1.0], size=(n, d)) * r
+            else:                                                         # one-sided
+                t = np.abs(rs.uniform(0.5, 1, size=(n, d))) * r
+            w = 10.0 ** rs.uniform(-6, 0, size=n)
+            B = ff.coefficients(t, w, P)
+            # offsets on the admission boundary z = 2 ln2 sum |s_k| r_k = zmax and inside it, all sign patterns
+            for frac in (1.0, 0.6, 0.2):
+                share = rs.dirichlet(np.ones(d))
+                s = share * (frac * zmax / (2 * ff.LN2)) / r * rs.choice([-1.0, 1.0], size=d)
+                z = 2 * ff.LN2 * float((np.abs(s) * r).sum())
+                assert z <= zmax * (1 + 1e-12)
+                want = ff.exact(t, w, s)
+                got = float(ff.evaluate(B, s))
+                if want > 1e-290:
+                    rel = abs(got - want) / want
+                    assert rel <= ff.remainder_bound(z, P) + 1e-11, (d, trial, frac, rel, ff.remainder_bound(z, P))   # + fp64 rounding of the model itself
+                    worst[d] = max(worst[d], rel)
+                    got32 = float(ff.evaluate({k: np.float32(v) for k, v in B.items()}, s.astype(np.float32), dtype=np.float32))
+                    if want > 1e-30:
+                        worst32[d] = max(worst32[d], abs(got32 - want) / want)
+    assert worst[1] <= 6e-7 and worst[2] <= 5e-6
+    # fp32: the exponent -|s|^2 alone carries ~|s|^2 2^-24 (the pair loop has the same term), the Horner chain the rest
+    assert worst32[1] <= 2e-5 and worst32[2] <= 3e-5, worst32
