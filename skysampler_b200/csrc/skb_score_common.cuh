@@ -557,8 +557,7 @@ __device__ __forceinline__ void home_superbox(const KdeDev* __restrict__ kde, co
             bool want = false;
             {
                 float lo[D], hi[D];
-#pragma unroll
-                for (int k = 0; k < 1; k++) load_box<D>(cbx + (size_t)cidx * 2 * D, lo, hi);
+                load_box<D>(cbx + (size_t)cidx * 2 * D, lo, hi);
 #pragma unroll
                 for (int q = 0; q < Q; q++) {
                     float lb = 0.f;
@@ -577,8 +576,7 @@ __device__ __forceinline__ void home_superbox(const KdeDev* __restrict__ kde, co
 #pragma unroll 1
             for (int sidx = cidx * CG; sidx < send; sidx++) {
                 float lo[D], hi[D];
-#pragma unroll
-                for (int k = 0; k < 1; k++) load_box<D>(sbx + (size_t)sidx * 2 * D, lo, hi);
+                load_box<D>(sbx + (size_t)sidx * 2 * D, lo, hi);
                 if (!(lo[0] <= hi[0])) continue;
 #pragma unroll
                 for (int q = 0; q < Q; q++) {
