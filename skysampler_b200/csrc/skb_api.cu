@@ -90,7 +90,7 @@ static std::atomic<int> g_opt_cull{env_int("SKB_NO_CULL", 0) ? 0 : 1};
 static std::atomic<int> g_opt_nsplit{env_int("SKB_FORCE_NSPLIT", 0)};
 static std::atomic<int> g_opt_stats{0};
 static std::atomic<int> g_opt_ff2_cells{-1};             // diagnostic: D == 2 cell records -1 auto / 0 off / 1 on
-static std::atomic<int> g_opt_kernel{env_int("SKB_KERNEL", 0)};     // 0: work-item-per-lane kernel; 1: round-1 culled kernels (A/B runs)
+static std::atomic<int> g_opt_kernel{env_int("SKB_KERNEL", 0)};     // 0: route by dimension; 1: single-launch kernels; 2: sorted-incidence pipeline (A/B runs)
 static unsigned long long* g_stats_dev[64] = {nullptr};
 
 }  // namespace skb

@@ -1,6 +1,7 @@
-// Device helpers shared by the score kernels (skb_score.cu: all-pairs and per-query-culling kernels; skb_wil.cu: the
-// work-item-per-lane kernel): packed fp32x2 PTX, mbarrier / TMA wrappers, the pair-term inner step, query loading with
-// the fused fp64 whitening, the exponent-reference search and the finalize epilogue.
+// Device helpers shared by the score kernels (skb_score.cu: 1-D far-field, lanes = queries and per-query-culling kernels;
+// skb_sparse.cu: the sorted-incidence pipeline): packed fp32x2 PTX, mbarrier / TMA wrappers, the pair-term inner step, query
+// loading with the fused fp64 whitening, box loads, the exponent-reference search (per lane and warp cooperative) and the
+// finalize epilogue.
 #pragma once
 #include "skb_internal.h"
 #include <math.h>
